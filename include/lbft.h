@@ -71,8 +71,9 @@ typedef struct lbft_instance_counters {
   uint32_t scheduled;         /* Simulator.event_count: creation stamps handed out                     */
   uint32_t max_active_round;  /* max over nodes of ActiveRound::active_round() (simulator.rs:86-88)     */
   uint32_t rng_draws;         /* Xoshiro256** next_u64 calls on the instance stream                    */
-  uint32_t max_queue;         /* high-water mark of the device event queue                             */
-  uint32_t reserved[3];
+  uint32_t max_queue;         /* high-water mark of the device event queue (implementation-specific)   */
+  uint32_t scheduled_notify;  /* DataSyncNotifyEvents handed a creation stamp (simulator.rs:348-354)    */
+  uint32_t reserved[2];
 } lbft_instance_counters;
 
 /* Device timing of the last lbft_run / lbft_run_device, measured with CUDA events on the stream the
@@ -130,6 +131,10 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim);
  * Returns LBFT_ERR_CAPACITY if any instance has a bit of LBFT_ST_ERROR_MASK set. */
 int lbft_run(lbft_sim* sim);
 
+/* Replace the seeds of the batch (a fresh `Simulator::new(seed, ..)` per instance on the next run);
+ * `seeds` is a host array of num_instances entries, copied into the handle's pinned staging buffer. */
+int lbft_set_seeds(lbft_sim* sim, const uint64_t* seeds);
+
 /* The same three phases separately, for callers that keep inputs resident in HBM (bench.py `value`). */
 int lbft_upload(lbft_sim* sim);     /* seeds host -> device                                  */
 int lbft_run_device(lbft_sim* sim); /* init + event loop + read-out kernels, no host copies  */
@@ -147,6 +152,11 @@ int lbft_status(lbft_sim* sim, uint32_t* out);
 int lbft_timing_info(lbft_sim* sim, lbft_timing* out);
 /* Bytes of device memory held by the handle, and the per-instance state footprint. */
 int lbft_memory_info(lbft_sim* sim, uint64_t* device_bytes, uint32_t* words_per_instance);
+
+/* Device address of a result buffer, for callers that consume results on the GPU (e.g. an NCCL
+ * all-gather of per-instance commit counts): which = 0 commit counts [I][N] u32, 1 last states [I][N]
+ * u64, 2 counters [I][12] u32, 3 status [I] u32.  Valid until lbft_destroy. */
+int lbft_device_buffer(lbft_sim* sim, uint32_t which, void** device_ptr, size_t* bytes);
 
 void lbft_destroy(lbft_sim* sim);
 const char* lbft_last_error(void);

@@ -1,0 +1,75 @@
+"""Build recipes for the native pieces (run by ``__graft_entry__.build()``).
+
+* ``csrc/liblbft_b200.so`` — the product: sm_100a CUDA kernels + the C ABI of ``include/lbft.h``.
+* ``oracle/liblbft_oracle.so`` and ``tests/hostcore/libhostcore.so`` — test infrastructure only.
+All artefacts are built in-tree (git-ignored, but they travel to the GPU box with the snapshot).
+"""
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "librabft_simulator_b200", "csrc")
+LIB_PATH = os.path.join(CSRC, "liblbft_b200.so")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_PATH = os.path.join(ORACLE_DIR, "liblbft_oracle.so")
+HOSTCORE_DIR = os.path.join(ROOT, "tests", "hostcore")
+HOSTCORE_PATH = os.path.join(HOSTCORE_DIR, "libhostcore.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _run(cmd, cwd):
+    proc = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), proc.stdout))
+    return proc.stdout
+
+
+def nvcc_path():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build_product(force=False, verbose_ptxas=False):
+    srcs = [os.path.join(CSRC, f) for f in ("lbft_api.cu", "sim_core.cuh", "sim_params.h", "host_setup.hpp")]
+    srcs.append(os.path.join(ROOT, "include", "lbft.h"))
+    if not force and _newer(LIB_PATH, srcs):
+        return LIB_PATH
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-o", LIB_PATH, "lbft_api.cu"]
+    out = _run(cmd, CSRC)
+    if verbose_ptxas:
+        print(out)
+    return LIB_PATH
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_capi.cpp", "oracle_selftest.cpp", "lbft_oracle.hpp")]
+    srcs.append(os.path.join(ROOT, "include", "lbft.h"))
+    if not force and _newer(ORACLE_PATH, srcs):
+        return ORACLE_PATH
+    _run(["make", "-B", "liblbft_oracle.so"], ORACLE_DIR)
+    return ORACLE_PATH
+
+
+def build_hostcore(force=False):
+    srcs = [os.path.join(HOSTCORE_DIR, "hostcore.cpp")] + [
+        os.path.join(CSRC, f) for f in ("sim_core.cuh", "sim_params.h", "host_setup.hpp")]
+    if not force and _newer(HOSTCORE_PATH, srcs):
+        return HOSTCORE_PATH
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+          "-o", HOSTCORE_PATH, "hostcore.cpp"], HOSTCORE_DIR)
+    return HOSTCORE_PATH
+
+
+def build_all(force=False):
+    return build_product(force), build_oracle(force), build_hostcore(force)

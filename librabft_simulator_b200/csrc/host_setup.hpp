@@ -1,0 +1,190 @@
+// host_setup.hpp — host-side preparation of a batched run: configuration validation, capacity
+// selection and the tables whose arithmetic must come from the host libm so that it matches what
+// the reference's Rust computes through the same libm (ln/sqrt/exp/pow), namely
+//   * RandomDelay::new mu/sigma ............................. bft-lib/src/simulator.rs:99-106
+//   * the rand_distr 0.4.0 ziggurat layer tables ............ (crate literals, "%.18f"-rounded)
+//   * PacemakerState::leader(round) for every round ......... librabft-v2/src/pacemaker.rs:100-109
+//                                                             + bft-lib/src/configuration.rs:65-75
+//   * PacemakerState::duration / query-all period per n ..... librabft-v2/src/pacemaker.rs:111-124,196
+// Pure C++ (no CUDA) so the CPU debugging harness in tests/hostcore can share it.  Written
+// independently of oracle/ (the oracle is the checker, not a dependency).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/lbft.h"
+#include "sim_params.h"
+
+namespace lbft {
+
+inline uint64_t host_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+// SipHash-1-3 (zero key) of one little-endian u64: `round.hash(&mut DefaultHasher::new())`.
+inline uint64_t siphash13_u64(uint64_t mword) {
+  uint64_t v0 = 0x736f6d6570736575ULL, v1 = 0x646f72616e646f6dULL, v2 = 0x6c7967656e657261ULL, v3 = 0x7465646279746573ULL;
+  auto rnd = [&]() {
+    v0 += v1; v1 = host_rotl(v1, 13); v1 ^= v0; v0 = host_rotl(v0, 32);
+    v2 += v3; v3 = host_rotl(v3, 16); v3 ^= v2;
+    v0 += v3; v3 = host_rotl(v3, 21); v3 ^= v0;
+    v2 += v1; v1 = host_rotl(v1, 17); v1 ^= v2; v2 = host_rotl(v2, 32);
+  };
+  v3 ^= mword; rnd(); v0 ^= mword;
+  uint64_t b = 8ULL << 56;
+  v3 ^= b; rnd(); v0 ^= b;
+  v2 ^= 0xff;
+  rnd(); rnd(); rnd();
+  return v0 ^ v1 ^ v2 ^ v3;
+}
+
+// EpochConfiguration::pick_author (configuration.rs:65-75): Xoshiro256** seeded through SplitMix64,
+// one rand-0.8 `gen_range(0..total_votes)` (widening-multiply rejection), weighted linear scan.
+inline uint32_t pick_author(const std::vector<uint32_t>& weights, uint64_t total, uint64_t seed) {
+  uint64_t s[4], x = seed;
+  for (int i = 0; i < 4; i++) {
+    x += 0x9e3779b97f4a7c15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    s[i] = z ^ (z >> 31);
+  }
+  uint64_t zone = (total << __builtin_clzll(total)) - 1, target;
+  for (;;) {
+    uint64_t v = host_rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = host_rotl(s[3], 45);
+    unsigned __int128 mm = (unsigned __int128)v * total;
+    if ((uint64_t)mm <= zone) { target = (uint64_t)(mm >> 64); break; }
+  }
+  for (uint32_t a = 0; a < weights.size(); a++) {
+    if (weights[a] > target) return a;
+    target -= weights[a];
+  }
+  return 0;  // unreachable
+}
+
+inline uint32_t pow2_ceil(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct HostSetup {
+  Params params{};  // pointer members are left null; the runtime fills in device addresses
+  std::vector<double> zig_x, zig_f;
+  std::vector<uint8_t> leader;
+  std::vector<int32_t> duration, period;
+  std::vector<uint32_t> weights;
+  std::string error;
+
+  bool build(const lbft_config& c) {
+    if (c.struct_size != sizeof(lbft_config)) return fail("lbft_config.struct_size does not match this library (ABI mismatch)");
+    if (c.num_instances == 0) return fail("num_instances must be > 0");
+    if (c.num_nodes < 1 || c.num_nodes > 64) return fail("num_nodes must be in 1..64");
+    if (!c.seeds) return fail("seeds must not be NULL");
+    if (c.max_clock < 0 || c.max_clock >= (1 << 29)) return fail("max_clock must be in [0, 2^29)");
+    if (c.flags != 0) return fail("flags must be 0");
+    if (c.commands_per_epoch == 0) return fail("commands_per_epoch must be > 0");
+    if (c.delta < 0 || c.target_commit_interval < 0) return fail("delta and target_commit_interval must be >= 0");
+    const uint32_t N = c.num_nodes;
+    Params& p = params;
+    p.num_instances = c.num_instances;
+    p.max_clock = (int32_t)c.max_clock;
+    p.delay_kind = c.delay_kind;
+    if (c.delay_kind == LBFT_DELAY_LOGNORMAL) {
+      if (!(c.delay_mean > 0.0) || !(c.delay_variance >= 0.0)) return fail("LogNormal delay needs mean > 0 and variance >= 0");
+      // simulator.rs:101-102
+      p.mu = std::log(c.delay_mean / std::sqrt(1.0 + c.delay_variance / (c.delay_mean * c.delay_mean)));
+      p.sigma = std::sqrt(std::log(1.0 + c.delay_variance / (c.delay_mean * c.delay_mean)));
+      p.delay_const = p.sigma == 0.0;
+      p.delay_const_value = p.delay_const ? (int64_t)std::exp(p.mu) : 0;
+      if (p.delay_const && (p.delay_const_value < 0 || p.delay_const_value > (1 << 29))) return fail("constant delay out of range");
+    } else if (c.delay_kind == LBFT_DELAY_UNIFORM) {
+      if (c.delay_lo < 0 || c.delay_hi < c.delay_lo || c.delay_hi > (1 << 29)) return fail("uniform delay needs 0 <= lo <= hi < 2^29");
+      p.uni_lo = (uint64_t)c.delay_lo;
+      p.uni_span = (uint64_t)(c.delay_hi - c.delay_lo + 1);
+    } else return fail("unknown delay_kind");
+    p.tci = (int32_t)(c.target_commit_interval > (1 << 30) ? (1 << 30) : c.target_commit_interval);
+    p.commands_per_epoch = c.commands_per_epoch > 0xffffffffULL ? 0xffffffffu : (uint32_t)c.commands_per_epoch;
+    // voting rights / quorum (configuration.rs:29-56; simulated_context.rs:209-216 = all 1)
+    weights.assign(N, 1);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < N; i++) {
+      if (c.voting_rights) {
+        if (c.voting_rights[i] > (1u << 24)) return fail("voting_rights entries must be <= 2^24");
+        weights[i] = (uint32_t)c.voting_rights[i];
+      }
+      total += weights[i];
+    }
+    if (total == 0) return fail("total voting rights must be > 0");
+    p.quorum = (uint32_t)(2 * total / 3 + 1);
+    p.silent_mask = 0;
+    if (c.silent)
+      for (uint32_t i = 0; i < N; i++)
+        if (c.silent[i]) p.silent_mask |= 1ULL << i;
+    p.part_max_len = c.partition_max_len;
+    if (c.partition_windows > 64) return fail("partition_windows must be <= 64");
+    // capacities
+    uint32_t rcap = c.round_cap ? c.round_cap : (uint32_t)(c.max_clock / 12 + 40);
+    rcap = (rcap + 31) / 32 * 32;
+    if (rcap < 32) rcap = 32;
+    if (rcap > 32768) return fail("round_cap must be <= 32768");
+    uint32_t qcap = c.queue_cap ? c.queue_cap : pow2_ceil(6 * N * N + 32);
+    if (qcap < rcap) qcap = rcap;  // the read-out kernel reuses the queue area as chain scratch
+    if (qcap > (1u << 20)) return fail("queue_cap too large");
+    uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 8 ? 64 : pow2_ceil(N * N));
+    if (pcap > 0xfff0u) return fail("payload_cap must be < 65520");
+    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows);
+    // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
+    leader.resize(rcap + 1);
+    for (uint32_t r = 0; r <= rcap; r++) leader[r] = (uint8_t)pick_author(weights, total, siphash13_u64(r));
+    // duration(n) = (delta as f64 * (n as f64).powf(gamma)) as i64; period = (lambda * duration as f64) as i64
+    duration.resize(rcap + 1);
+    period.resize(rcap + 1);
+    for (uint32_t n = 0; n <= rcap; n++) {
+      double dv = (double)c.delta * std::pow((double)n, c.gamma);
+      int64_t dur = std::isnan(dv) ? 0 : (dv >= 9.2e18 ? INT64_MAX : (dv <= -9.2e18 ? INT64_MIN : (int64_t)dv));
+      double pv = c.lambda * (double)dur;
+      int64_t per = std::isnan(pv) ? 0 : (pv >= 9.2e18 ? INT64_MAX : (pv <= -9.2e18 ? INT64_MIN : (int64_t)pv));
+      const int64_t CL = 1 << 30;  // any deadline beyond max_clock (< 2^29) behaves identically
+      duration[n] = (int32_t)(dur > CL ? CL : (dur < -CL ? -CL : dur));
+      period[n] = (int32_t)(per > CL ? CL : (per < -CL ? -CL : per));
+    }
+    build_ziggurat();
+    return true;
+  }
+
+  // rand_distr 0.4.0 ziggurat_tables.rs (ZIG_NORM_X / ZIG_NORM_F / ZIG_NORM_R): regenerated with the
+  // crate's generator recurrence and passed through the "%.18f" decimal literals it ships.
+  void build_ziggurat() {
+    const double R = 3.6541528853610088, V = 0.00492867323399;
+    std::vector<double> xs(257);
+    auto f = [](double t) { return std::exp(-t * t / 2.0); };
+    xs[0] = V / f(R);
+    xs[1] = R;
+    for (int i = 2; i < 256; i++) xs[i] = std::sqrt(-2.0 * std::log(V / xs[i - 1] + f(xs[i - 1])));
+    xs[256] = 0.0;
+    auto lit = [](double v) {
+      char buf[64];
+      snprintf(buf, sizeof buf, "%.18f", v);
+      return strtod(buf, nullptr);
+    };
+    zig_x.resize(257);
+    zig_f.resize(257);
+    for (int i = 0; i <= 256; i++) {
+      zig_x[i] = lit(xs[i]);
+      zig_f[i] = lit(f(xs[i]));
+    }
+    params.zig_r = lit(R);
+  }
+
+ private:
+  bool fail(const char* msg) {
+    error = msg;
+    return false;
+  }
+};
+
+}  // namespace lbft

@@ -1,0 +1,379 @@
+// lbft_api.cu — the C ABI of include/lbft.h over the sm_100a event-loop kernel.
+//
+// Replaces, for a whole batch of instances at once, the reference call sequence
+//   Simulator::new(seed, nodes, RandomDelay::new(mean, variance), context_factory)   simulator.rs:200-250
+//   sim.loop_until(GlobalTime(max_clock), None)                                      simulator.rs:380-475
+//   contexts[i].committed_history() / last_committed_state()                         simulated_context.rs:98-100,194-196
+// (callers: librabft-v2/src/main.rs:36-53, librabft-v2/tests/simulated_run.rs:19-94).
+// There is no CPU fallback: without a usable CUDA device every entry point fails with LBFT_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lbft.h"
+#include "host_setup.hpp"
+#include "sim_core.cuh"
+
+using namespace lbft;
+
+#define LBFT_SAME(a, b) ((uint32_t)(a) == (uint32_t)(b))
+static_assert(LBFT_SAME(ST_DONE, LBFT_ST_DONE) && LBFT_SAME(ST_ROUND_OVERFLOW, LBFT_ST_ROUND_OVERFLOW) &&
+                  LBFT_SAME(ST_QUEUE_OVERFLOW, LBFT_ST_QUEUE_OVERFLOW) && LBFT_SAME(ST_PAYLOAD_OVERFLOW, LBFT_ST_PAYLOAD_OVERFLOW) &&
+                  LBFT_SAME(ST_INVARIANT, LBFT_ST_INVARIANT) && LBFT_SAME(ST_EPOCH_CHANGE, LBFT_ST_EPOCH_CHANGE) &&
+                  LBFT_SAME(ST_DELAY_NEAR_INT, LBFT_ST_DELAY_NEAR_INT) && LBFT_SAME(ST_TIME_OVERFLOW, LBFT_ST_TIME_OVERFLOW),
+              "status bits out of sync with include/lbft.h");
+static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter layout");
+
+// ---------------------------------------------------------------------------------------------
+// Kernel: one thread per simulator instance, one warp per 32-instance tile.
+// Block = 1 warp so that the 2048 tiles of a 65 536-instance batch spread evenly over 148 SMs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBlockThreads = 32;
+
+template <int NMAX>
+__global__ void __launch_bounds__(kBlockThreads) lbft_event_loop_kernel(const __grid_constant__ Params P) {
+  __shared__ double s_zx[257];
+  __shared__ double s_zf[257];
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) {
+    s_zx[i] = P.zig_x[i];
+    s_zf[i] = P.zig_f[i];
+  }
+  __syncthreads();
+  const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= P.num_instances) return;
+  const uint32_t tile = inst >> 5, lane = inst & 31;
+  TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32 + lane};
+  Core<TileMem<32>, NMAX> core(P, mem, s_zx, s_zf);
+  core.init(P.seeds[inst]);
+  core.run();
+  core.finalize(inst);
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int set_error(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return set_error(LBFT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+struct lbft_sim {
+  HostSetup hs;
+  Params P{};
+  int device = 0;
+  uint32_t I = 0, N = 0;
+  std::vector<uint64_t> seeds_host;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  // device buffers
+  uint64_t* d_seeds = nullptr;
+  double* d_zx = nullptr;
+  double* d_zf = nullptr;
+  uint8_t* d_leader = nullptr;
+  int32_t* d_duration = nullptr;
+  int32_t* d_period = nullptr;
+  uint32_t* d_weights = nullptr;
+  uint32_t* d_state = nullptr;
+  uint32_t* d_commit_counts = nullptr;
+  uint32_t* d_lc_round = nullptr;
+  uint64_t* d_last_state = nullptr;
+  uint32_t* d_counters = nullptr;
+  uint32_t* d_status = nullptr;
+  uint64_t device_bytes = 0;
+  // pinned host mirrors of the outputs
+  uint64_t* h_seeds = nullptr;
+  uint32_t* h_commit_counts = nullptr;
+  uint32_t* h_lc_round = nullptr;
+  uint64_t* h_last_state = nullptr;
+  uint32_t* h_counters = nullptr;
+  uint32_t* h_status = nullptr;
+  bool uploaded = false, ran = false, downloaded = false;
+  lbft_timing timing{};
+};
+
+template <class T>
+static cudaError_t dev_alloc(lbft_sim* s, T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e == cudaSuccess) s->device_bytes += count * sizeof(T);
+  return e;
+}
+
+static void free_all(lbft_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->d_seeds); cudaFree(s->d_zx); cudaFree(s->d_zf); cudaFree(s->d_leader); cudaFree(s->d_duration);
+  cudaFree(s->d_period); cudaFree(s->d_weights); cudaFree(s->d_state); cudaFree(s->d_commit_counts);
+  cudaFree(s->d_lc_round); cudaFree(s->d_last_state); cudaFree(s->d_counters); cudaFree(s->d_status);
+  cudaFreeHost(s->h_seeds); cudaFreeHost(s->h_commit_counts); cudaFreeHost(s->h_lc_round);
+  cudaFreeHost(s->h_last_state); cudaFreeHost(s->h_counters); cudaFreeHost(s->h_status);
+  for (auto& e : s->ev)
+    if (e) cudaEventDestroy(e);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+extern "C" {
+
+uint32_t lbft_abi_version(void) { return LBFT_ABI_VERSION; }
+const char* lbft_last_error(void) { return g_last_error.c_str(); }
+
+int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
+  if (!config || !out_sim) return set_error(LBFT_ERR_INVALID, "config and out_sim must not be NULL");
+  *out_sim = nullptr;
+  lbft_sim* s = new (std::nothrow) lbft_sim();
+  if (!s) return set_error(LBFT_ERR_NOMEM, "out of host memory");
+  if (!s->hs.build(*config)) {
+    std::string e = s->hs.error;
+    delete s;
+    return set_error(LBFT_ERR_INVALID, e);
+  }
+  s->I = config->num_instances;
+  s->N = config->num_nodes;
+  s->device = config->device;
+  s->seeds_host.assign(config->seeds, config->seeds + s->I);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    delete s;
+    return set_error(LBFT_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  }
+  if (s->device < 0 || s->device >= ndev) {
+    delete s;
+    return set_error(LBFT_ERR_INVALID, "device ordinal out of range");
+  }
+#define CREATE_TRY(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t e2_ = (expr);                                                                 \
+    if (e2_ != cudaSuccess) {                                                                 \
+      std::string m_ = std::string(#expr) + ": " + cudaGetErrorString(e2_);                 \
+      free_all(s);                                                                            \
+      return set_error(e2_ == cudaErrorMemoryAllocation ? LBFT_ERR_NOMEM : LBFT_ERR_CUDA, m_); \
+    }                                                                                         \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(s->device));
+  CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  for (auto& evt : s->ev) CREATE_TRY(cudaEventCreate(&evt));
+  const Layout& L = s->hs.params.L;
+  const size_t I = s->I, N = s->N, tiles = (I + 31) / 32;
+  CREATE_TRY(dev_alloc(s, &s->d_seeds, I));
+  CREATE_TRY(dev_alloc(s, &s->d_zx, 257));
+  CREATE_TRY(dev_alloc(s, &s->d_zf, 257));
+  CREATE_TRY(dev_alloc(s, &s->d_leader, L.round_cap + 1));
+  CREATE_TRY(dev_alloc(s, &s->d_duration, L.round_cap + 1));
+  CREATE_TRY(dev_alloc(s, &s->d_period, L.round_cap + 1));
+  CREATE_TRY(dev_alloc(s, &s->d_weights, N));
+  CREATE_TRY(dev_alloc(s, &s->d_state, tiles * L.total_words * 32));
+  CREATE_TRY(dev_alloc(s, &s->d_commit_counts, I * N));
+  CREATE_TRY(dev_alloc(s, &s->d_lc_round, I * N));
+  CREATE_TRY(dev_alloc(s, &s->d_last_state, I * N));
+  CREATE_TRY(dev_alloc(s, &s->d_counters, I * 12));
+  CREATE_TRY(dev_alloc(s, &s->d_status, I));
+  CREATE_TRY(cudaMallocHost((void**)&s->h_seeds, I * sizeof(uint64_t)));
+  CREATE_TRY(cudaMallocHost((void**)&s->h_commit_counts, I * N * sizeof(uint32_t)));
+  CREATE_TRY(cudaMallocHost((void**)&s->h_lc_round, I * N * sizeof(uint32_t)));
+  CREATE_TRY(cudaMallocHost((void**)&s->h_last_state, I * N * sizeof(uint64_t)));
+  CREATE_TRY(cudaMallocHost((void**)&s->h_counters, I * 12 * sizeof(uint32_t)));
+  CREATE_TRY(cudaMallocHost((void**)&s->h_status, I * sizeof(uint32_t)));
+  memcpy(s->h_seeds, s->seeds_host.data(), I * sizeof(uint64_t));
+  // launch-invariant tables
+  CREATE_TRY(cudaMemcpy(s->d_zx, s->hs.zig_x.data(), 257 * sizeof(double), cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_zf, s->hs.zig_f.data(), 257 * sizeof(double), cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_leader, s->hs.leader.data(), L.round_cap + 1, cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_duration, s->hs.duration.data(), (L.round_cap + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_period, s->hs.period.data(), (L.round_cap + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_weights, s->hs.weights.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+#undef CREATE_TRY
+  s->P = s->hs.params;
+  s->P.seeds = s->d_seeds;
+  s->P.zig_x = s->d_zx;
+  s->P.zig_f = s->d_zf;
+  s->P.leader = s->d_leader;
+  s->P.duration = s->d_duration;
+  s->P.period = s->d_period;
+  s->P.weights = s->d_weights;
+  s->P.state = s->d_state;
+  s->P.out_commit_counts = s->d_commit_counts;
+  s->P.out_lc_round = s->d_lc_round;
+  s->P.out_last_state = s->d_last_state;
+  s->P.out_counters = s->d_counters;
+  s->P.out_status = s->d_status;
+  *out_sim = s;
+  return LBFT_OK;
+}
+
+int lbft_set_seeds(lbft_sim* s, const uint64_t* seeds) {
+  if (!s || !seeds) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  memcpy(s->h_seeds, seeds, (size_t)s->I * sizeof(uint64_t));
+  s->uploaded = false;
+  return LBFT_OK;
+}
+
+int lbft_device_buffer(lbft_sim* s, uint32_t which, void** device_ptr, size_t* bytes) {
+  if (!s || !device_ptr || !bytes) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  const size_t I = s->I, N = s->N;
+  switch (which) {
+    case 0: *device_ptr = s->d_commit_counts; *bytes = I * N * sizeof(uint32_t); break;
+    case 1: *device_ptr = s->d_last_state; *bytes = I * N * sizeof(uint64_t); break;
+    case 2: *device_ptr = s->d_counters; *bytes = I * 12 * sizeof(uint32_t); break;
+    case 3: *device_ptr = s->d_status; *bytes = I * sizeof(uint32_t); break;
+    default: return set_error(LBFT_ERR_INVALID, "unknown buffer id");
+  }
+  return LBFT_OK;
+}
+
+int lbft_upload(lbft_sim* s) {
+  if (!s) return set_error(LBFT_ERR_INVALID, "sim must not be NULL");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->d_seeds, s->h_seeds, s->I * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+  s->timing.h2d_ms = ms;
+  s->timing.h2d_bytes = s->I * sizeof(uint64_t);
+  s->uploaded = true;
+  return LBFT_OK;
+}
+
+int lbft_run_device(lbft_sim* s) {
+  if (!s) return set_error(LBFT_ERR_INVALID, "sim must not be NULL");
+  if (!s->uploaded) return set_error(LBFT_ERR_STATE, "lbft_upload must be called before lbft_run_device");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const uint32_t blocks = (s->I + kBlockThreads - 1) / kBlockThreads;
+  CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+  if (s->N <= 16) lbft_event_loop_kernel<16><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  else if (s->N <= 32) lbft_event_loop_kernel<32><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  else lbft_event_loop_kernel<64><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]));
+  s->timing.init_ms = 0;
+  s->timing.sim_ms = ms;
+  s->timing.finalize_ms = 0;
+  s->timing.kernel_launches = 1;
+  s->ran = true;
+  s->downloaded = false;
+  return LBFT_OK;
+}
+
+int lbft_download(lbft_sim* s) {
+  if (!s) return set_error(LBFT_ERR_INVALID, "sim must not be NULL");
+  if (!s->ran) return set_error(LBFT_ERR_STATE, "nothing has been run yet");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const size_t I = s->I, N = s->N;
+  CUDA_TRY(cudaEventRecord(s->ev[4], s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_commit_counts, s->d_commit_counts, I * N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_lc_round, s->d_lc_round, I * N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_last_state, s->d_last_state, I * N * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, I * 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_status, s->d_status, I * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, s->ev[4], s->ev[5]));
+  s->timing.d2h_ms = ms;
+  s->timing.d2h_bytes = I * N * (2 * sizeof(uint32_t) + sizeof(uint64_t)) + I * 13 * sizeof(uint32_t);
+  s->downloaded = true;
+  for (size_t i = 0; i < I; i++)
+    if (s->h_status[i] & LBFT_ST_ERROR_MASK) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "instance %zu ended with status 0x%x (see lbft_status; raise round_cap/queue_cap/payload_cap)", i,
+               s->h_status[i]);
+      return set_error(LBFT_ERR_CAPACITY, buf);
+    }
+  return LBFT_OK;
+}
+
+int lbft_run(lbft_sim* s) {
+  int r = lbft_upload(s);
+  if (r != LBFT_OK) return r;
+  r = lbft_run_device(s);
+  if (r != LBFT_OK) return r;
+  return lbft_download(s);
+}
+
+static int need_results(lbft_sim* s, const void* out) {
+  if (!s || !out) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  if (!s->downloaded) return set_error(LBFT_ERR_STATE, "results are not available: call lbft_run (or lbft_download) first");
+  return LBFT_OK;
+}
+int lbft_commit_counts(lbft_sim* s, uint32_t* out) {
+  if (int r = need_results(s, out)) return r;
+  memcpy(out, s->h_commit_counts, (size_t)s->I * s->N * sizeof(uint32_t));
+  return LBFT_OK;
+}
+int lbft_last_states(lbft_sim* s, uint64_t* out) {
+  if (int r = need_results(s, out)) return r;
+  memcpy(out, s->h_last_state, (size_t)s->I * s->N * sizeof(uint64_t));
+  return LBFT_OK;
+}
+int lbft_counters(lbft_sim* s, lbft_instance_counters* out) {
+  if (int r = need_results(s, out)) return r;
+  memcpy(out, s->h_counters, (size_t)s->I * 12 * sizeof(uint32_t));
+  return LBFT_OK;
+}
+int lbft_status(lbft_sim* s, uint32_t* out) {
+  if (int r = need_results(s, out)) return r;
+  memcpy(out, s->h_status, (size_t)s->I * sizeof(uint32_t));
+  return LBFT_OK;
+}
+int lbft_timing_info(lbft_sim* s, lbft_timing* out) {
+  if (!s || !out) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  *out = s->timing;
+  return LBFT_OK;
+}
+int lbft_memory_info(lbft_sim* s, uint64_t* device_bytes, uint32_t* words_per_instance) {
+  if (!s) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  if (device_bytes) *device_bytes = s->device_bytes;
+  if (words_per_instance) *words_per_instance = s->P.L.total_words;
+  return LBFT_OK;
+}
+
+// committed_history() of one node: walk the instance's chain table backwards from the node's last
+// committed round (every commit extends the previous one by exactly one block,
+// simulated_context.rs:172-174, so the log is the ancestor chain of the last committed block).
+int lbft_commit_log(lbft_sim* s, uint32_t instance, uint32_t node, lbft_commit* out, size_t cap, size_t* n) {
+  if (!s || !n) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  if (!s->downloaded) return set_error(LBFT_ERR_STATE, "results are not available: call lbft_run first");
+  if (instance >= s->I || node >= s->N) return set_error(LBFT_ERR_INVALID, "instance/node out of range");
+  if (cap && !out) return set_error(LBFT_ERR_INVALID, "out must not be NULL when cap > 0");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const Layout& L = s->P.L;
+  std::vector<uint32_t> chain(2 * (size_t)L.round_cap);
+  const uint32_t tile = instance >> 5, lane = instance & 31;
+  const uint32_t* src = s->d_state + ((size_t)tile * L.total_words + L.chain_base) * 32 + lane;
+  CUDA_TRY(cudaMemcpy2D(chain.data(), sizeof(uint32_t), src, 32 * sizeof(uint32_t), sizeof(uint32_t), chain.size(), cudaMemcpyDeviceToHost));
+  uint32_t lc = s->h_lc_round[(size_t)instance * s->N + node];
+  uint32_t count = s->h_commit_counts[(size_t)instance * s->N + node];
+  std::vector<lbft_commit> log(count);
+  uint32_t i = count;
+  for (uint32_t r = lc; r != 0 && i > 0; r = chain[2 * r] & 0xffffu) {
+    if (r >= L.round_cap) return set_error(LBFT_ERR_STATE, "corrupt chain table");
+    --i;
+    log[i].proposer = s->hs.leader[r];
+    log[i].index = chain[2 * r] >> 16;
+    log[i].time = (int64_t)(int32_t)chain[2 * r + 1];
+  }
+  if (i != 0) return set_error(LBFT_ERR_STATE, "chain shorter than the commit count");
+  *n = count;
+  for (size_t k = 0; k < count && k < cap; k++) out[k] = log[k];
+  return LBFT_OK;
+}
+
+void lbft_destroy(lbft_sim* s) { free_all(s); }
+
+}  // extern "C"

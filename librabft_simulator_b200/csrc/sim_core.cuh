@@ -1,0 +1,870 @@
+// sim_core.cuh — the per-instance LibraBFTv2 discrete-event loop in "round-id form".
+//
+// One Core object simulates ONE instance (one `Simulator<NodeState<SimulatedContext>, ...>` of the
+// reference) and is driven by one GPU thread; 32 instances share a warp tile (sim_params.h).  The
+// code is __host__ __device__ so the same source can be compiled with g++ for CPU-side debugging
+// in tests/hostcore (test infrastructure only — the product library never runs it on the host).
+//
+// What is restated here (reference = /root/reference, novifinancial/librabft_simulator):
+//   event loop, ordering, timers, fan-out ....... bft-lib/src/simulator.rs:149-161, 200-269, 296-475
+//   NodeState::update_node, commits, tracker .... librabft-v2/src/node.rs:179-202, 240-396
+//   record store (verify/insert/QC/TC/3-chain) .. librabft-v2/src/record_store.rs:207-255, 257-541, 557-738
+//   pacemaker ................................... librabft-v2/src/pacemaker.rs:100-124, 142-207
+//   data-sync notification / request / response . librabft-v2/src/data_sync.rs:82-240
+//   fake ledger (fetch/compute/commit) .......... bft-lib/src/simulated_context.rs:102-197
+//   third-party arithmetic (rand 0.8.3, rand_distr 0.4.0, rand_xoshiro 0.6.0, SipHash-1-3): see
+//   SURVEY.md Appendix A; restated independently of oracle/.
+//
+// Round-id form (every assumption is checked at run time and raises
+// LBFT_ST_INVARIANT if violated): honest leaders produce at most one block and one QC per round per
+// instance, so blocks/QCs/states are identified by their round; the per-instance chain table holds
+// {previous QC round, command index, proposer-local time} per round, and each node keeps three
+// per-round bitsets (block known, QC known, state pending) instead of hash maps.  Request/Response
+// events carry no payload because the reference answers a request on the requester itself
+// (simulator.rs:446), which makes the response a no-op for the record store.
+#pragma once
+#include <stdint.h>
+
+#include "sim_params.h"
+
+#if defined(__CUDACC__)
+#define LBFT_HD __host__ __device__ __forceinline__
+#else
+#define LBFT_HD inline
+#include <cmath>
+#endif
+
+namespace lbft {
+
+// Status bits — keep in sync with include/lbft.h (static_asserted in lbft_api.cu).
+enum : uint32_t {
+  ST_DONE = 1u << 0,
+  ST_ROUND_OVERFLOW = 1u << 1,
+  ST_QUEUE_OVERFLOW = 1u << 2,
+  ST_PAYLOAD_OVERFLOW = 1u << 3,
+  ST_INVARIANT = 1u << 4,
+  ST_EPOCH_CHANGE = 1u << 5,
+  ST_DELAY_NEAR_INT = 1u << 6,
+  ST_TIME_OVERFLOW = 1u << 7,
+  ST_FATAL = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST_TIME_OVERFLOW
+};
+
+constexpr int32_t NODE_TIME_NEVER = 0x7fffffff;
+constexpr uint32_t PAY_NONE = 0xffffu;
+
+// ---- small portability layer -----------------------------------------------------------------
+LBFT_HD uint32_t clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)x);
+#else
+  return (uint32_t)__builtin_clz(x);
+#endif
+}
+LBFT_HD uint32_t clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clzll((long long)x);
+#else
+  return (uint32_t)__builtin_clzll(x);
+#endif
+}
+LBFT_HD uint32_t ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)(__ffsll((long long)x) - 1);
+#else
+  return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+LBFT_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+// IEEE double ops that must NOT be contracted into FMAs (the reference's Rust never fuses).
+LBFT_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a * b;  // host harness is built with -ffp-contract=off
+#endif
+}
+LBFT_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+LBFT_HD double bits_to_f64(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  double d;
+  __builtin_memcpy(&d, &b, 8);
+  return d;
+#endif
+}
+LBFT_HD uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+// SipHash-1-3 with a zero key over a stream of u64 words (Rust DefaultHasher; the state key of
+// simulated_context.rs:51-55 only ever feeds whole 8-byte integers).
+struct SipWords {
+  uint64_t v0, v1, v2, v3, nbytes;
+  LBFT_HD SipWords() : v0(0x736f6d6570736575ULL), v1(0x646f72616e646f6dULL), v2(0x6c7967656e657261ULL), v3(0x7465646279746573ULL), nbytes(0) {}
+  LBFT_HD void round() {
+    v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32);
+    v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;
+    v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;
+    v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32);
+  }
+  LBFT_HD void write_u64(uint64_t m) { v3 ^= m; round(); v0 ^= m; nbytes += 8; }
+  LBFT_HD uint64_t finish() {
+    uint64_t b = nbytes << 56;
+    v3 ^= b; round(); v0 ^= b;
+    v2 ^= 0xff;
+    round(); round(); round();
+    return v0 ^ v1 ^ v2 ^ v3;
+  }
+};
+
+// Strided view of one instance's words inside its warp tile.
+template <int STRIDE>
+struct TileMem {
+  uint32_t* base;  // already offset to the instance's lane
+  LBFT_HD uint32_t ld(uint32_t w) const { return base[(size_t)w * STRIDE]; }
+  LBFT_HD void st(uint32_t w, uint32_t v) const { base[(size_t)w * STRIDE] = v; }
+};
+
+// List of authors used for the shuffled fan-out (simulator.rs:326-343, 356-370).
+template <int NMAX>
+struct AuthorList;
+template <>
+struct AuthorList<16> {  // nibble-packed, lives in one 64-bit register
+  uint64_t v = 0;
+  uint32_t len = 0;
+  LBFT_HD void push(uint32_t a) { v |= (uint64_t)a << (4 * len); len++; }
+  LBFT_HD uint32_t get(uint32_t i) const { return (uint32_t)(v >> (4 * i)) & 15u; }
+  LBFT_HD void swap(uint32_t i, uint32_t j) {
+    uint64_t d = ((v >> (4 * i)) ^ (v >> (4 * j))) & 15u;
+    v ^= (d << (4 * i)) | (d << (4 * j));
+  }
+};
+template <>
+struct AuthorList<64> {
+  uint8_t a[64];
+  uint32_t len = 0;
+  LBFT_HD void push(uint32_t x) { a[len++] = (uint8_t)x; }
+  LBFT_HD uint32_t get(uint32_t i) const { return a[i]; }
+  LBFT_HD void swap(uint32_t i, uint32_t j) { uint8_t t = a[i]; a[i] = a[j]; a[j] = t; }
+};
+
+struct Actions {  // NodeUpdateActions, interfaces.rs:12-21 (should_send holds at most one author)
+  int32_t next;
+  int32_t send_to;
+  bool broadcast, query_all;
+};
+
+template <class Mem, int NMAX>
+struct Core {
+  const Params& P;
+  const Layout& L;
+  Mem m;
+  const double* zx;
+  const double* zf;
+  // ---- per-instance registers ----
+  uint64_t s0, s1, s2, s3;  // Xoshiro256** (simulator.rs:32)
+  uint32_t draws;
+  uint32_t stamp;  // Simulator.event_count / creation stamps
+  uint32_t qsize;
+  uint32_t status;
+  int32_t clock;  // Simulator.clock
+  uint32_t pay_free, pay_next;
+  uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify;
+
+  LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_) : P(p), L(p.L), m(mem), zx(zx_), zf(zf_) {}
+
+  // ------------------------------------------------------------------------------------------
+  // RNG (rand_xoshiro 0.6.0 / rand 0.8.3 / rand_distr 0.4.0)
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD void seed_rng(uint64_t seed, uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d) const {
+    uint64_t x = seed, out[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      x += 0x9e3779b97f4a7c15ULL;
+      uint64_t z = x;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+      out[i] = z ^ (z >> 31);
+    }
+    a = out[0]; b = out[1]; c = out[2]; d = out[3];
+  }
+  LBFT_HD uint64_t next_u64() {
+    draws++;
+    uint64_t result = rotl64(s1 * 5, 7) * 9;
+    uint64_t t = s1 << 17;
+    s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3;
+    s2 ^= t;
+    s3 = rotl64(s3, 45);
+    return result;
+  }
+  LBFT_HD uint32_t gen_range_u32(uint32_t n) {  // UniformInt<u32>::sample_single_inclusive(0, n-1)
+    uint32_t zone = (n << clz32(n)) - 1;
+    for (;;) {
+      uint32_t v = (uint32_t)(next_u64() >> 32);
+      uint64_t mm = (uint64_t)v * n;
+      if ((uint32_t)mm <= zone) return (uint32_t)(mm >> 32);
+    }
+  }
+  LBFT_HD uint64_t gen_range_u64(uint64_t n) {
+    uint64_t zone = (n << clz64(n)) - 1;
+    for (;;) {
+      uint64_t v = next_u64();
+      uint64_t lo = v * n;
+      if (lo <= zone) return mulhi64(v, n);
+    }
+  }
+  LBFT_HD double open01() { return bits_to_f64((1023ULL << 52) | (next_u64() >> 12)) - (1.0 - 2.220446049250313e-16 / 2.0); }
+  LBFT_HD double standard_normal() {  // rand_distr ziggurat, 256 layers
+    for (;;) {
+      uint64_t bits = next_u64();
+      uint32_t i = (uint32_t)bits & 0xffu;
+      double u = bits_to_f64((1024ULL << 52) | (bits >> 12)) - 3.0;
+      double xi = zx[i], xi1 = zx[i + 1];
+      double x = mul_rn(u, xi);
+      if (fabs(x) < xi1) return x;
+      if (i == 0) {
+        double xx = 1.0, yy = 0.0;
+        while (mul_rn(-2.0, yy) < mul_rn(xx, xx)) {
+          double a = open01();
+          double b = open01();
+          xx = log(a) / P.zig_r;
+          yy = log(b);
+        }
+        return u < 0.0 ? xx - P.zig_r : P.zig_r - xx;
+      }
+      double g = mul_rn((double)(next_u64() >> 11), 1.0 / 9007199254740992.0);
+      double f0 = zf[i], f1 = zf[i + 1];
+      double lhs = add_rn(f1, mul_rn(f0 - f1, g));
+      double rhs = exp(mul_rn(-x, x) / 2.0);
+      if (lhs < rhs) return x;
+    }
+  }
+  // GlobalTime::add_delay (simulator.rs:110-118): returns the delay in ms.
+  LBFT_HD int32_t sample_delay() {
+    if (P.delay_kind == 1u) return (int32_t)(P.uni_lo + gen_range_u64(P.uni_span));
+    double z = standard_normal();
+    if (P.delay_const) return (int32_t)P.delay_const_value;  // sigma == 0: exp(mu) evaluated by the host libm
+    double v = exp(add_rn(P.mu, mul_rn(P.sigma, z)));
+    double r = rint(v);
+    if (fabs(v - r) < 1e-9 * (r > 1.0 ? r : 1.0)) status |= ST_DELAY_NEAR_INT;
+    if (!(v < 1.0e9)) { status |= ST_TIME_OVERFLOW; return 1000000000; }
+    return (int32_t)(int64_t)v;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // memory helpers
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD uint32_t nbase(uint32_t n) const { return L.node_base + n * L.node_words; }
+  LBFT_HD uint64_t ld_mask(uint32_t w) const {
+    uint64_t v = m.ld(w);
+    if (NMAX > 32) v |= (uint64_t)m.ld(w + 1) << 32;
+    return v;
+  }
+  LBFT_HD void st_mask(uint32_t w, uint64_t v) const {
+    m.st(w, (uint32_t)v);
+    if (NMAX > 32) m.st(w + 1, (uint32_t)(v >> 32));
+  }
+  LBFT_HD uint32_t ld_u16(uint32_t w, uint32_t i) const { return (m.ld(w + (i >> 1)) >> (16 * (i & 1))) & 0xffffu; }
+  LBFT_HD void st_u16(uint32_t w, uint32_t i, uint32_t v) const {
+    uint32_t x = m.ld(w + (i >> 1));
+    uint32_t sh = 16 * (i & 1);
+    m.st(w + (i >> 1), (x & ~(0xffffu << sh)) | (v << sh));
+  }
+  LBFT_HD bool bit_test(uint32_t w, uint32_t r) const { return (m.ld(w + (r >> 5)) >> (r & 31)) & 1u; }
+  LBFT_HD void bit_set(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) | (1u << (r & 31))); }
+  LBFT_HD void bit_clear(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) & ~(1u << (r & 31))); }
+  LBFT_HD uint32_t chain_prev(uint32_t r) const { return m.ld(L.chain_base + 2 * r) & 0xffffu; }
+
+  struct NodeRegs {
+    uint32_t f[F_NSCALAR];
+  };
+  LBFT_HD void load_node(uint32_t n, NodeRegs& d) const {
+    uint32_t b = nbase(n);
+#pragma unroll
+    for (int i = 0; i < (int)F_NSCALAR; i++) d.f[i] = m.ld(b + i);
+  }
+  LBFT_HD void store_node(uint32_t n, const NodeRegs& d) const {
+    uint32_t b = nbase(n);
+#pragma unroll
+    for (int i = 0; i < (int)F_NSCALAR; i++) m.st(b + i, d.f[i]);
+  }
+  LBFT_HD static uint32_t election(const NodeRegs& d) { return (d.f[F_FLAGS] & FL_ELECTION_MASK) >> FL_ELECTION_SHIFT; }
+  LBFT_HD static void set_election(NodeRegs& d, uint32_t e) { d.f[F_FLAGS] = (d.f[F_FLAGS] & ~FL_ELECTION_MASK) | (e << FL_ELECTION_SHIFT); }
+  LBFT_HD static uint32_t leader_of(const NodeRegs& d) { return (d.f[F_FLAGS] >> FL_LEADER_SHIFT) & 0xffu; }
+
+  // ------------------------------------------------------------------------------------------
+  // pending-event queue: binary min-heap on (time, 3-kind, stamp)  (simulator.rs:149-161)
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD uint64_t heap_key_at(uint32_t i) const { return ((uint64_t)m.ld(L.heap_time + i) << 32) | m.ld(L.heap_key + i); }
+  LBFT_HD void heap_move(uint32_t dst, uint32_t src) const {
+    m.st(L.heap_time + dst, m.ld(L.heap_time + src));
+    m.st(L.heap_key + dst, m.ld(L.heap_key + src));
+    m.st(L.heap_data + dst, m.ld(L.heap_data + src));
+  }
+  // schedule_event (simulator.rs:252-264).  Events beyond max_clock can never be popped before the
+  // loop ends (:389-391): they consume their creation stamp and are dropped.  Returns true if queued.
+  LBFT_HD bool push_event(int32_t time, uint32_t kind, uint32_t data) {
+    uint32_t st = stamp++;
+    if (stamp >= (1u << 30)) status |= ST_QUEUE_OVERFLOW;
+    if (time > P.max_clock) return false;
+    if (qsize >= L.queue_cap) { status |= ST_QUEUE_OVERFLOW; return false; }
+    uint32_t klo = ((3u - kind) << 30) | st;
+    uint64_t key = ((uint64_t)(uint32_t)time << 32) | klo;
+    uint32_t i = qsize++;
+    if (qsize > max_queue) max_queue = qsize;
+    while (i > 0) {
+      uint32_t p = (i - 1) >> 1;
+      if (heap_key_at(p) <= key) break;
+      heap_move(i, p);
+      i = p;
+    }
+    m.st(L.heap_time + i, (uint32_t)time);
+    m.st(L.heap_key + i, klo);
+    m.st(L.heap_data + i, data);
+    return true;
+  }
+  LBFT_HD void pop_event(int32_t& time, uint32_t& kind, uint32_t& data) {
+    time = (int32_t)m.ld(L.heap_time);
+    uint32_t klo = m.ld(L.heap_key);
+    data = m.ld(L.heap_data);
+    kind = 3u - (klo >> 30);
+    uint32_t n = --qsize;
+    if (n == 0) return;
+    uint32_t lt = m.ld(L.heap_time + n), lk = m.ld(L.heap_key + n), ld_ = m.ld(L.heap_data + n);
+    uint64_t key = ((uint64_t)lt << 32) | lk;
+    uint32_t i = 0;
+    for (;;) {
+      uint32_t c = 2 * i + 1;
+      if (c >= n) break;
+      uint64_t kc = heap_key_at(c);
+      if (c + 1 < n) {
+        uint64_t kr = heap_key_at(c + 1);
+        if (kr < kc) { kc = kr; c = c + 1; }
+      }
+      if (key <= kc) break;
+      heap_move(i, c);
+      i = c;
+    }
+    m.st(L.heap_time + i, lt);
+    m.st(L.heap_key + i, lk);
+    m.st(L.heap_data + i, ld_);
+  }
+
+  // notification payload pool (DataSyncNotification snapshots, shared by all receivers of one send)
+  LBFT_HD uint32_t pay_alloc() {
+    uint32_t s;
+    if (pay_free != PAY_NONE) {
+      s = pay_free;
+      pay_free = m.ld(L.pay_base + s * L.pay_words + 2) & 0xffffu;
+    } else if (pay_next < L.payload_cap) {
+      s = pay_next++;
+    } else {
+      status |= ST_PAYLOAD_OVERFLOW;
+      s = PAY_NONE;
+    }
+    return s;
+  }
+  LBFT_HD void pay_release(uint32_t s) {  // link into the free list through word [2]
+    m.st(L.pay_base + s * L.pay_words + 2, pay_free);
+    pay_free = s;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // record store in round-id form
+  // ------------------------------------------------------------------------------------------
+  // update_current_round, record_store.rs:207-219
+  LBFT_HD void update_current_round(uint32_t n, NodeRegs& d, uint32_t round) {
+    if (round <= d.f[F_CUR]) return;
+    if (round >= L.round_cap) { status |= ST_ROUND_OVERFLOW; return; }
+    d.f[F_CUR] = round;
+    d.f[F_FLAGS] &= ~(FL_PROPOSED | FL_ELECTION_MASK);
+    st_mask(nbase(n) + L.n_tmask, 0);
+    st_mask(nbase(n) + L.n_vmask, 0);
+    d.f[F_TOW] = 0;
+    d.f[F_BALLOT] = 0;
+  }
+  // Is the execution state of the block certified by QC `prev` (0 = the epoch's initial state)
+  // available to SimulatedContext::compute?  simulated_context.rs:102-108, 128-157
+  LBFT_HD bool state_available(uint32_t n, const NodeRegs& d, uint32_t prev) const {
+    if (d.f[F_LC_ROUND] == prev) return true;
+    if (prev == 0) return false;
+    return bit_test(nbase(n) + L.n_pend, prev);
+  }
+  // Record::Block — verify :263-291, insert :466-476
+  LBFT_HD void insert_block(uint32_t n, NodeRegs& d, uint32_t r) {
+    uint32_t b = nbase(n);
+    if (bit_test(b + L.n_hasblk, r)) return;  // "Block was already inserted."
+    uint32_t prev = chain_prev(r);
+    if (prev != 0 && !bit_test(b + L.n_hasqc, prev)) return;  // "The previous QC (if any) must be verified first."
+    // rounds are increasing by construction (the proposer's hqc round is below its current round)
+    if (r == d.f[F_CUR]) d.f[F_FLAGS] |= FL_PROPOSED;  // author == leader(round) by construction (C.1)
+    bit_set(b + L.n_hasblk, r);
+  }
+  // Record::Vote — verify :292-329, insert :477-499
+  LBFT_HD void insert_vote(uint32_t n, NodeRegs& d, uint32_t r, uint32_t author) {
+    uint32_t b = nbase(n);
+    if (r != d.f[F_CUR]) return;
+    if (!bit_test(b + L.n_hasblk, r)) return;
+    uint64_t vm = ld_mask(b + L.n_vmask);
+    if ((vm >> author) & 1) return;
+    st_mask(b + L.n_vmask, vm | (1ULL << author));
+    if (election(d) == 0) {
+      d.f[F_BALLOT] += P.weights[author];
+      if (d.f[F_BALLOT] >= P.quorum) set_election(d, 1);
+    }
+  }
+  // Record::QuorumCertificate — verify :330-389, insert :500-526
+  LBFT_HD void insert_qc(uint32_t n, NodeRegs& d, uint32_t r) {
+    uint32_t b = nbase(n);
+    if (bit_test(b + L.n_hasqc, r)) return;    // "QuorumCertificate was already inserted."
+    if (!bit_test(b + L.n_hasblk, r)) return;  // "The certified block hash of a QC must be verified first."
+    bit_set(b + L.n_hasqc, r);                 // inserted before execution (:505)
+    uint32_t prev = chain_prev(r);
+    if (!state_available(n, d, prev)) return;  // "I failed to execute a block with a QC" — QC stays in the map
+    bit_set(b + L.n_pend, r);
+    if (r > d.f[F_HQC]) d.f[F_HQC] = r;
+    update_current_round(n, d, r + 1);
+    // update_commit_3chain_round :221-235
+    if (prev != 0) {
+      uint32_t r1 = chain_prev(prev);
+      if (r1 != 0 && r == prev + 1 && prev == r1 + 1 && r1 > d.f[F_HCR]) {
+        d.f[F_HCR] = r1;
+        d.f[F_HCC] = r;
+      }
+    }
+  }
+  // Record::Timeout — verify :390-415, insert :527-538
+  LBFT_HD void insert_timeout(uint32_t n, NodeRegs& d, uint32_t round, uint32_t hcbr, uint32_t author) {
+    uint32_t b = nbase(n);
+    if (hcbr > d.f[F_HQC]) return;
+    if (round != d.f[F_CUR]) return;
+    uint64_t tm = ld_mask(b + L.n_tmask);
+    if ((tm >> author) & 1) return;
+    tm |= 1ULL << author;
+    st_mask(b + L.n_tmask, tm);
+    st_u16(b + L.n_thcbr, author, hcbr);
+    d.f[F_TOW] += P.weights[author];
+    if (d.f[F_TOW] >= P.quorum) {
+      st_mask(b + L.n_tcmask, tm);
+      for (uint32_t i = 0; i < L.hcbr_words; i++) m.st(b + L.n_tchcbr + i, m.ld(b + L.n_thcbr + i));
+      d.f[F_TC_ROUND] = d.f[F_CUR];
+      d.f[F_FLAGS] |= FL_HAS_TC;
+      d.f[F_HTC] = d.f[F_CUR];
+      update_current_round(n, d, d.f[F_CUR] + 1);
+    }
+  }
+  // propose_block :655-674 (+ CommandFetcher::fetch, simulated_context.rs:116-125)
+  LBFT_HD void propose_block(uint32_t n, NodeRegs& d, uint32_t prev_round, int32_t clk) {
+    uint32_t idx = d.f[F_NEXT_CMD]++;
+    uint32_t r = d.f[F_CUR];
+    if (idx > 0xffffu) status |= ST_ROUND_OVERFLOW;
+    if (bit_test(L.created_base, r)) status |= ST_INVARIANT;  // App. C.1: second block in a round
+    bit_set(L.created_base, r);
+    m.st(L.chain_base + 2 * r, prev_round | (idx << 16));
+    m.st(L.chain_base + 2 * r + 1, (uint32_t)clk);
+    insert_block(n, d, r);
+  }
+  // create_vote :676-700
+  LBFT_HD bool create_vote(uint32_t n, NodeRegs& d, uint32_t r) {
+    uint32_t prev = chain_prev(r);
+    if (!state_available(n, d, prev)) return false;
+    bit_set(nbase(n) + L.n_pend, r);
+    insert_vote(n, d, r, n);
+    return true;
+  }
+  // check_for_new_quorum_certificate :702-738
+  LBFT_HD bool check_for_new_qc(uint32_t n, NodeRegs& d) {
+    if (election(d) != 1) return false;
+    uint32_t r = d.f[F_CUR];
+    if (P.leader[r] != n) return false;
+    set_election(d, 2);
+    if (bit_test(L.qcmade_base, r)) status |= ST_INVARIANT;  // App. C.1: second QC in a round
+    bit_set(L.qcmade_base, r);
+    insert_qc(n, d, r);
+    return true;
+  }
+  // process_commits node.rs:313-350 over committed_states_after record_store.rs:557-574 and
+  // StateFinalizer::commit simulated_context.rs:161-185
+  LBFT_HD void process_commits(uint32_t n, NodeRegs& d) {
+    uint32_t after = d.f[F_TRK_HCR];
+    uint32_t top = d.f[F_HCC] ? d.f[F_HCR] : 0;
+    while (top > after) {
+      uint32_t q = top;
+      for (;;) {
+        uint32_t p = chain_prev(q);
+        if (p <= after) break;
+        q = p;
+      }
+      uint32_t b = nbase(n);
+      if (!bit_test(b + L.n_pend, q)) status |= ST_INVARIANT;   // "Committed states should be known"
+      bit_clear(b + L.n_pend, q);
+      if (chain_prev(q) != d.f[F_LC_ROUND]) status |= ST_INVARIANT;  // happened_just_before
+      d.f[F_LC_ROUND] = q;
+      d.f[F_COMMITS]++;
+      if (d.f[F_COMMITS] >= P.commands_per_epoch) status |= ST_EPOCH_CHANGE;  // read_epoch_id would change
+      after = q;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // NodeState::update_node, node.rs:240-304
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD Actions update_node(uint32_t n, NodeRegs& d, int32_t clk) {
+    Actions a;
+    a.next = NODE_TIME_NEVER;
+    a.send_to = -1;
+    a.broadcast = false;
+    a.query_all = false;
+    const uint32_t b = nbase(n);
+    // ---- Pacemaker::update_pacemaker, pacemaker.rs:142-207
+    uint32_t active = (d.f[F_HQC] > d.f[F_HTC] ? d.f[F_HQC] : d.f[F_HTC]) + 1;
+    if (active > d.f[F_PMR]) {
+      d.f[F_PMR] = active;
+      d.f[F_PM_START] = (uint32_t)clk;
+      uint32_t ld = P.leader[active];
+      d.f[F_FLAGS] = (d.f[F_FLAGS] & ~(0xffu << FL_LEADER_SHIFT)) | (ld << FL_LEADER_SHIFT);
+      uint32_t base = d.f[F_HCR] > 0 ? d.f[F_HCR] + 2 : 0;  // duration(), :111-124
+      if (!(active > base)) { status |= ST_INVARIANT; base = active - 1; }
+      d.f[F_PM_DUR] = (uint32_t)P.duration[active - base];
+      d.f[F_PM_PERIOD] = (uint32_t)P.period[active - base];
+      if (ld != n) a.send_to = (int32_t)ld;
+    }
+    const uint32_t leader = leader_of(d);
+    bool propose = false, mk_timeout = false;
+    bool proposed_some = d.f[F_CUR] == d.f[F_PMR] && (d.f[F_FLAGS] & FL_PROPOSED);  // proposed_block(), record_store.rs:611-634
+    if (leader == n && !proposed_some) {
+      propose = true;
+      a.broadcast = true;
+      a.next = clk;
+    }
+    bool has_timeout = active == d.f[F_CUR] && ((ld_mask(b + L.n_tmask) >> n) & 1);
+    if (!has_timeout) {
+      int32_t deadline = (int32_t)d.f[F_PM_START] + (int32_t)d.f[F_PM_DUR];
+      if (clk >= deadline) {
+        mk_timeout = true;
+        a.broadcast = true;
+      } else if (deadline < a.next) a.next = deadline;
+    } else {
+      int32_t period = (int32_t)d.f[F_PM_PERIOD];
+      int32_t qd = (int32_t)d.f[F_LQA] + period;
+      if (clk >= qd) {
+        a.query_all = true;
+        qd = clk + period;
+      }
+      if (qd < a.next) a.next = qd;
+    }
+    // ---- process_pacemaker_actions, node.rs:179-202
+    if (mk_timeout && propose) status |= ST_INVARIANT;  // App. C.1b
+    if (mk_timeout) {
+      insert_timeout(n, d, active, d.f[F_HQC], n);  // create_timeout, record_store.rs:636-649
+      if (active > d.f[F_LVR]) d.f[F_LVR] = active;
+    }
+    if (propose) propose_block(n, d, d.f[F_HQC], clk);
+    // ---- vote on the proposal, node.rs:255-276
+    if (d.f[F_CUR] == d.f[F_PMR] && (d.f[F_FLAGS] & FL_PROPOSED)) {
+      uint32_t r = d.f[F_CUR];
+      uint32_t prev = chain_prev(r);  // previous_round(), record_store.rs:588-598
+      if (r > d.f[F_LVR] && prev >= d.f[F_LOCKED]) {
+        d.f[F_LVR] = r;
+        uint32_t sp = prev ? chain_prev(prev) : 0;  // second_previous_round(), :600-609
+        if (sp > d.f[F_LOCKED]) d.f[F_LOCKED] = sp;
+        if (create_vote(n, d, r)) a.send_to = (int32_t)leader;
+      }
+    }
+    // ---- QC creation, node.rs:277-283
+    if (check_for_new_qc(n, d)) {
+      a.broadcast = true;
+      a.next = clk;
+    }
+    process_commits(n, d);
+    // ---- CommitTracker::update_tracker, node.rs:364-396
+    if (d.f[F_HCR] > d.f[F_TRK_HCR]) {
+      d.f[F_TRK_HCR] = d.f[F_HCR];
+      d.f[F_TRK_TIME] = (uint32_t)clk;
+    }
+    int32_t tl = (int32_t)d.f[F_TRK_TIME] > (int32_t)d.f[F_LQA] ? (int32_t)d.f[F_TRK_TIME] : (int32_t)d.f[F_LQA];
+    int32_t deadline = tl + P.tci;
+    if (clk >= deadline) {
+      a.query_all = true;
+      deadline = clk + P.tci;
+    }
+    if (deadline < a.next) a.next = deadline;
+    if (a.query_all) d.f[F_LQA] = (uint32_t)clk;
+    return a;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // DataSyncNode::create_notification (data_sync.rs:82-111) into a payload slot
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD void write_notification(uint32_t n, const NodeRegs& d, uint32_t slot, uint32_t refs) {
+    uint32_t pb = L.pay_base + slot * L.pay_words, b = nbase(n);
+    uint64_t tm = ld_mask(b + L.n_tmask);
+    bool has_tc = d.f[F_FLAGS] & FL_HAS_TC;
+    uint32_t vote = (uint32_t)((ld_mask(b + L.n_vmask) >> n) & 1);  // current_vote(author), record_store.rs:762-764
+    uint32_t prop = (d.f[F_CUR] == d.f[F_PMR] && (d.f[F_FLAGS] & FL_PROPOSED) && leader_of(d) == n) ? 1u : 0u;
+    m.st(pb + 0, d.f[F_HCC] | (d.f[F_HQC] << 16));
+    m.st(pb + 1, d.f[F_CUR] | ((has_tc ? d.f[F_TC_ROUND] : 0u) << 16));
+    m.st(pb + 2, refs | ((vote | (prop << 1)) << 16));
+    st_mask(pb + L.p_tcmask, has_tc ? ld_mask(b + L.n_tcmask) : 0);
+    st_mask(pb + L.p_curmask, tm);
+    for (uint32_t i = 0; i < L.hcbr_words; i++) {
+      m.st(pb + L.p_tchcbr + i, m.ld(b + L.n_tchcbr + i));
+      m.st(pb + L.p_curhcbr + i, m.ld(b + L.n_thcbr + i));
+    }
+  }
+  // DataSyncNode::handle_notification (data_sync.rs:113-177).  Returns should_sync.
+  LBFT_HD bool handle_notification(uint32_t n, NodeRegs& d, uint32_t slot, uint32_t sender) {
+    uint32_t pb = L.pay_base + slot * L.pay_words;
+    uint32_t w0 = m.ld(pb), w1 = m.ld(pb + 1), w2 = m.ld(pb + 2);
+    uint32_t hcc = w0 & 0xffffu, hqc = w0 >> 16, cur_s = w1 & 0xffffu, tc_round = w1 >> 16;
+    bool vote = (w2 >> 16) & 1, prop = (w2 >> 17) & 1;
+    bool should_sync = false;
+    if (hcc) {
+      insert_qc(n, d, hcc);
+      should_sync |= hcc > d.f[F_HCR] + 2;
+    }
+    if (hqc) {
+      insert_qc(n, d, hqc);
+      should_sync |= hqc > d.f[F_HQC];
+    }
+    if (prop) insert_block(n, d, cur_s);
+    // timeouts: the TC's first, then the sender's current ones, ascending author.
+    // A group whose round is not the receiver's current round is rejected wholesale, and accepting
+    // a timeout can only move the receiver's round away from the group's round.
+    if (tc_round && tc_round == d.f[F_CUR]) {
+      uint64_t mask = ld_mask(pb + L.p_tcmask);
+      while (mask) {
+        uint32_t a = ctz64(mask);
+        mask &= mask - 1;
+        insert_timeout(n, d, tc_round, ld_u16(pb + L.p_tchcbr, a), a);
+      }
+    }
+    if (cur_s == d.f[F_CUR]) {
+      uint64_t mask = ld_mask(pb + L.p_curmask);
+      while (mask) {
+        uint32_t a = ctz64(mask);
+        mask &= mask - 1;
+        insert_timeout(n, d, cur_s, ld_u16(pb + L.p_curhcbr, a), a);
+      }
+    }
+    if (vote) insert_vote(n, d, cur_s, sender);
+    // release our reference on the payload
+    uint32_t refs = (w2 & 0xffffu) - 1;
+    if (refs == 0) pay_release(slot);
+    else m.st(pb + 2, (w2 & 0xffff0000u) | refs);
+    return should_sync;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Simulator::process_node_actions, simulator.rs:296-378
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD bool partitioned(uint32_t a, uint32_t b2) const {  // EXTENSION
+    for (uint32_t k = 0; k < L.part_windows; k++) {
+      int32_t t0 = (int32_t)m.ld(L.part_base + 4 * k), t1 = (int32_t)m.ld(L.part_base + 4 * k + 1);
+      uint64_t mask = m.ld(L.part_base + 4 * k + 2) | ((uint64_t)m.ld(L.part_base + 4 * k + 3) << 32);
+      if (clock >= t0 && clock < t1 && (((mask >> a) ^ (mask >> b2)) & 1)) return true;
+    }
+    return false;
+  }
+  // schedule_network_event :266-269 (+ partition drop).  Returns true if the event was queued.
+  LBFT_HD bool schedule_network_event(uint32_t kind, uint32_t receiver, uint32_t sender, uint32_t slot) {
+    int32_t t = clock + sample_delay();
+    if (L.part_windows && partitioned(receiver, sender)) {
+      stamp++;
+      return false;
+    }
+    return push_event(t, kind, receiver | (sender << 8) | (slot << 16));
+  }
+  LBFT_HD void push_timer(uint32_t n, NodeRegs& d, int32_t t) {
+    if ((uint32_t)t == d.f[F_LAST_TIMER]) {
+      // An UpdateTimerEvent for (n, t) is already pending with a smaller stamp.  The duplicate could
+      // only ever be popped right after it (same time) and be cancelled by
+      // ignore_scheduled_updates_until (simulator.rs:403-410) with no side effect: account for it
+      // as popped+cancelled now and do not queue it.
+      stamp++;
+      if (t <= P.max_clock) { proc3++; cancelled++; }
+      return;
+    }
+    d.f[F_LAST_TIMER] = (uint32_t)t;
+    push_event(t, EV_TIMER, n | (n << 8) | (PAY_NONE << 16));
+  }
+  LBFT_HD void process_node_actions(uint32_t n, NodeRegs& d, const Actions& a) {
+    const uint32_t N = L.num_nodes;
+    // next UpdateTimerEvent :311-324
+    int64_t from_node = a.next == NODE_TIME_NEVER ? (int64_t)0x7fffffff : (int64_t)a.next + (int32_t)d.f[F_STARTUP];
+    int64_t nt = from_node > (int64_t)clock + 1 ? from_node : (int64_t)clock + 1;
+    if (nt > 0x7ffffff0) nt = 0x7ffffff0;
+    d.f[F_IGNORE] = (uint32_t)((int32_t)nt - 1);
+    push_timer(n, d, (int32_t)nt);
+    // notifications :326-354
+    AuthorList<(NMAX <= 16 ? 16 : 64)> recv;
+    if (a.broadcast) {
+      for (uint32_t i = 0; i < N; i++)
+        if (i != n) recv.push(i);
+    } else if (a.send_to >= 0 && (uint32_t)a.send_to != n) {
+      recv.push((uint32_t)a.send_to);
+    }
+    for (uint32_t i = recv.len; i-- > 1;) recv.swap(i, gen_range_u32(i + 1));  // SliceRandom::shuffle
+    if (recv.len) {
+      uint32_t slot = pay_alloc();
+      uint32_t queued = 0;
+      sched_notify += recv.len;
+      for (uint32_t i = 0; i < recv.len; i++)
+        if (schedule_network_event(EV_NOTIFY, recv.get(i), n, slot)) queued++;
+      if (slot != PAY_NONE) {
+        if (queued) write_notification(n, d, slot, queued);
+        else pay_release(slot);
+      }
+    }
+    // requests :356-377
+    if (a.query_all) {
+      AuthorList<(NMAX <= 16 ? 16 : 64)> snd;
+      for (uint32_t i = 0; i < N; i++)
+        if (i != n) snd.push(i);
+      for (uint32_t i = snd.len; i-- > 1;) snd.swap(i, gen_range_u32(i + 1));
+      for (uint32_t i = 0; i < snd.len; i++) schedule_network_event(EV_REQUEST, n, snd.get(i), PAY_NONE);
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Simulator::new, simulator.rs:200-250 (+ make_initial_state node.rs:87-114, record_store.rs:169-198)
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD void init(uint64_t seed) {
+    const uint32_t N = L.num_nodes;
+    seed_rng(seed, s0, s1, s2, s3);
+    draws = 0; stamp = 0; qsize = 0; status = 0; clock = 0;
+    pay_free = PAY_NONE; pay_next = 0;
+    proc0 = proc1 = proc2 = proc3 = cancelled = max_queue = sched_notify = 0;
+    for (uint32_t w = 0; w < N * L.node_words; w++) m.st(L.node_base + w, 0);
+    for (uint32_t w = 0; w < 2 * L.rset_words; w++) m.st(L.created_base + w, 0);
+    // EXTENSION D.3: partition plan from a separate stream; must match oracle_capi.cpp make_partition_plan
+    if (L.part_windows) {
+      uint64_t k0 = s0, k1 = s1, k2 = s2, k3 = s3;
+      uint32_t kd = draws;
+      seed_rng(seed ^ 0xD1B54A32D192ED03ULL, s0, s1, s2, s3);
+      uint64_t nsub = N >= 64 ? 0xfffffffffffffffeULL : ((1ULL << N) - 2);
+      for (uint32_t k = 0; k < L.part_windows; k++) {
+        int64_t t0 = (int64_t)gen_range_u64((uint64_t)P.max_clock + 1);
+        int64_t len = 1 + (int64_t)gen_range_u64(P.part_max_len ? P.part_max_len : 1);
+        uint64_t mask = N >= 2 ? 1 + gen_range_u64(nsub) : 0;
+        m.st(L.part_base + 4 * k, (uint32_t)t0);
+        m.st(L.part_base + 4 * k + 1, (uint32_t)(t0 + len));
+        m.st(L.part_base + 4 * k + 2, (uint32_t)mask);
+        m.st(L.part_base + 4 * k + 3, (uint32_t)(mask >> 32));
+      }
+      s0 = k0; s1 = k1; s2 = k2; s3 = k3;
+      draws = kd;
+    }
+    for (uint32_t n = 0; n < N; n++) {
+      int32_t startup = sample_delay() + 1;
+      uint32_t b = nbase(n);
+      m.st(b + F_STARTUP, (uint32_t)startup);
+      m.st(b + F_IGNORE, (uint32_t)(startup - 1));
+      m.st(b + F_CUR, 1);
+      m.st(b + F_FLAGS, FL_LEADER_NONE << FL_LEADER_SHIFT);
+      m.st(b + F_LAST_TIMER, (uint32_t)startup);
+      push_event(startup, EV_TIMER, n | (n << 8) | (PAY_NONE << 16));
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Simulator::loop_until, simulator.rs:380-475
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD void run() {
+    while (qsize > 0 && !(status & ST_FATAL)) {
+      int32_t t;
+      uint32_t kind, data;
+      pop_event(t, kind, data);
+      if (t > P.max_clock) break;  // unreachable: such events are dropped at push
+      if (t > clock) clock = t;
+      uint32_t receiver = data & 0xffu, sender = (data >> 8) & 0xffu, slot = data >> 16;
+      if (kind == EV_NOTIFY) proc0++;
+      else if (kind == EV_REQUEST) proc1++;
+      else if (kind == EV_RESPONSE) proc2++;
+      else proc3++;
+      // EXTENSION D.2: silent nodes handle nothing and answer no request
+      if (P.silent_mask) {
+        bool drop = (P.silent_mask >> receiver) & 1;
+        if (kind == EV_REQUEST && ((P.silent_mask >> sender) & 1)) drop = true;
+        if (drop) {
+          if (kind == EV_NOTIFY) {  // still release the payload reference
+            uint32_t pb = L.pay_base + slot * L.pay_words;
+            uint32_t w2 = m.ld(pb + 2), refs = (w2 & 0xffffu) - 1;
+            if (refs == 0) pay_release(slot);
+            else m.st(pb + 2, (w2 & 0xffff0000u) | refs);
+          }
+          continue;
+        }
+      }
+      if (kind == EV_REQUEST) {
+        // answered by `receiver` itself (simulator.rs:446): no state change, one delay draw
+        schedule_network_event(EV_RESPONSE, receiver, sender, PAY_NONE);
+        continue;
+      }
+      NodeRegs d;
+      load_node(receiver, d);
+      if (kind == EV_TIMER && clock <= (int32_t)d.f[F_IGNORE]) {
+        cancelled++;
+        continue;
+      }
+      bool should_sync = false;
+      if (kind == EV_NOTIFY) should_sync = handle_notification(receiver, d, slot, sender);
+      Actions a = update_node(receiver, d, clock - (int32_t)d.f[F_STARTUP]);
+      if (should_sync) schedule_network_event(EV_REQUEST, receiver, sender, PAY_NONE);  // :427-433
+      process_node_actions(receiver, d, a);
+      store_node(receiver, d);
+    }
+    if (!(status & ST_FATAL)) status |= ST_DONE;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // read-out: commit counts, last committed round and state key per node; counters; status
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD void finalize(uint32_t inst) {
+    const uint32_t N = L.num_nodes;
+    uint32_t max_round = 0;
+    for (uint32_t n = 0; n < N; n++) {
+      uint32_t b = nbase(n);
+      uint32_t commits = m.ld(b + F_COMMITS), lc = m.ld(b + F_LC_ROUND), pmr = m.ld(b + F_PMR);
+      if (pmr > max_round) max_round = pmr;
+      // lay the chain out in commit order in the (now dead) event queue area, then hash it:
+      // SimulatedLedgerState::key, simulated_context.rs:51-55
+      uint32_t depth = 0;
+      for (uint32_t r = lc; r != 0; r = chain_prev(r)) depth++;
+      if (depth != commits) status |= ST_INVARIANT;
+      uint32_t i = depth;
+      for (uint32_t r = lc; r != 0 && i > 0; r = chain_prev(r)) m.st(L.heap_time + (--i), r);
+      SipWords h;
+      h.write_u64(depth);
+      for (uint32_t k = 0; k < depth; k++) {
+        uint32_t r = m.ld(L.heap_time + k);
+        uint32_t c0 = m.ld(L.chain_base + 2 * r);
+        int32_t tm = (int32_t)m.ld(L.chain_base + 2 * r + 1);
+        h.write_u64(P.leader[r]);
+        h.write_u64(c0 >> 16);
+        h.write_u64((uint64_t)(int64_t)tm);
+      }
+      P.out_commit_counts[(size_t)inst * N + n] = commits;
+      P.out_lc_round[(size_t)inst * N + n] = lc;
+      P.out_last_state[(size_t)inst * N + n] = h.finish();
+    }
+    uint32_t* c = P.out_counters + (size_t)inst * 12;
+    c[0] = proc0; c[1] = proc1; c[2] = proc2; c[3] = proc3;
+    c[4] = cancelled; c[5] = stamp; c[6] = max_round; c[7] = draws; c[8] = max_queue;
+    c[9] = sched_notify; c[10] = 0; c[11] = 0;
+    P.out_status[inst] = status;
+  }
+};
+
+}  // namespace lbft

@@ -1,0 +1,145 @@
+// sim_params.h — launch-uniform parameters and the per-instance HBM layout of the batched
+// LibraBFTv2 simulator.  Shared by the host runtime (lbft_api.cu) and the device core
+// (sim_core.cuh).  Plain C++ (no CUDA types) so that the host test harness can include it too.
+//
+// HBM layout ("warp tiles"): instances are grouped 32 to a tile; a tile is `total_words` rows of
+// 32 u32 lanes, i.e. word w of the instance in lane l of tile t lives at
+//      state[(t * total_words + w) * 32 + l].
+// Whenever the 32 lanes of a warp touch the same logical word, the access is one fully coalesced
+// 128-byte line; a tile is one contiguous (total_words * 128)-byte extent that a single bulk copy
+// can stage into shared memory.
+#pragma once
+#include <stdint.h>
+
+namespace lbft {
+
+enum : uint32_t { EV_NOTIFY = 0, EV_REQUEST = 1, EV_RESPONSE = 2, EV_TIMER = 3 };
+
+// Per-node scalar fields, one u32 word each (node.rs:28-45, record_store.rs:93-119,
+// pacemaker.rs:58-78, simulator.rs:53-59, simulated_context.rs:74-83 in round-id form).
+enum NodeField : uint32_t {
+  F_STARTUP = 0,   // SimulatedNode.startup_time (global ms)
+  F_IGNORE,        // SimulatedNode.ignore_scheduled_updates_until
+  F_CUR,           // record_store.current_round
+  F_HQC,           // highest_quorum_certificate_round (QC identified by its round)
+  F_HTC,           // highest_timeout_certificate_round
+  F_HCR,           // highest_committed_round
+  F_HCC,           // round of highest_commit_certificate (0 = None)
+  F_LVR,           // node.latest_voted_round
+  F_LOCKED,        // node.locked_round
+  F_PMR,           // pacemaker.active_round
+  F_PM_START,      // pacemaker.active_round_start_time (node-local ms)
+  F_PM_DUR,        // pacemaker.active_round_duration
+  F_PM_PERIOD,     // (lambda * duration) as i64
+  F_LQA,           // node.latest_query_all_time
+  F_TRK_HCR,       // tracker.highest_committed_round
+  F_TRK_TIME,      // tracker.latest_commit_time
+  F_FLAGS,         // bit0 current_proposed_block.is_some, bits1-2 election, bit3 has TC, bits8-15 active_leader (0xff None)
+  F_NEXT_CMD,      // context.next_fetched_command_index
+  F_LC_ROUND,      // round of the block whose state is last_committed_ledger_state (0 = genesis)
+  F_COMMITS,       // committed_history().len()
+  F_BALLOT,        // weight of votes for the (single) block of the current round
+  F_TOW,           // current_timeouts_weight
+  F_TC_ROUND,      // round of highest_timeout_certificate
+  F_LAST_TIMER,    // time of the most recently pushed UpdateTimerEvent (for exact de-duplication)
+  F_NSCALAR
+};
+enum : uint32_t {
+  FL_PROPOSED = 1u,
+  FL_ELECTION_SHIFT = 1,  // 0 Ongoing, 1 Won, 2 Closed
+  FL_ELECTION_MASK = 3u << 1,
+  FL_HAS_TC = 1u << 3,
+  FL_LEADER_SHIFT = 8,
+  FL_LEADER_NONE = 0xffu
+};
+
+struct Layout {
+  uint32_t num_nodes;
+  uint32_t mask_words;   // 1 (N<=32) or 2 (N<=64): author bitmasks
+  uint32_t hcbr_words;   // ceil(N/2): per-author u16 highest_certified_block_round of a timeout
+  uint32_t rset_words;   // round_cap/32: per-round bitsets
+  uint32_t round_cap, queue_cap, payload_cap, part_windows;
+  // word offsets inside a node block
+  uint32_t n_vmask, n_tmask, n_tcmask, n_thcbr, n_tchcbr, n_hasblk, n_hasqc, n_pend, node_words;
+  // word offsets inside an instance
+  uint32_t node_base, created_base /* per-round "block exists" / "QC exists" bitsets */, qcmade_base, chain_base,
+      part_base, heap_time, heap_key, heap_data, pay_base, pay_words, total_words;
+  // payload slot: [0] hcc | hqc<<16  [1] cur_round | tc_round<<16  [2] refcount | flags<<16 (bit0 vote, bit1 proposal)
+  //               [3..] tc mask, cur mask, tc hcbr[], cur hcbr[]
+  uint32_t p_tcmask, p_curmask, p_tchcbr, p_curhcbr;
+};
+
+inline Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows) {
+  Layout L{};
+  L.num_nodes = N;
+  L.mask_words = N > 32 ? 2 : 1;
+  L.hcbr_words = (N + 1) / 2;
+  L.round_cap = round_cap;
+  L.rset_words = round_cap / 32;
+  L.queue_cap = queue_cap;
+  L.payload_cap = payload_cap;
+  L.part_windows = part_windows;
+  uint32_t w = F_NSCALAR;
+  L.n_vmask = w; w += L.mask_words;
+  L.n_tmask = w; w += L.mask_words;
+  L.n_tcmask = w; w += L.mask_words;
+  L.n_thcbr = w; w += L.hcbr_words;
+  L.n_tchcbr = w; w += L.hcbr_words;
+  L.n_hasblk = w; w += L.rset_words;
+  L.n_hasqc = w; w += L.rset_words;
+  L.n_pend = w; w += L.rset_words;
+  L.node_words = w;
+  uint32_t o = 0;
+  L.node_base = o; o += N * L.node_words;
+  L.created_base = o; o += L.rset_words;
+  L.qcmade_base = o; o += L.rset_words;
+  L.chain_base = o; o += 2 * round_cap;  // [2r] prev | cmd<<16, [2r+1] time
+  L.part_base = o; o += 4 * part_windows;  // t0, t1, mask lo, mask hi
+  L.heap_time = o; o += queue_cap;
+  L.heap_key = o; o += queue_cap;
+  L.heap_data = o; o += queue_cap;
+  L.p_tcmask = 3;
+  L.p_curmask = L.p_tcmask + L.mask_words;
+  L.p_tchcbr = L.p_curmask + L.mask_words;
+  L.p_curhcbr = L.p_tchcbr + L.hcbr_words;
+  L.pay_words = L.p_curhcbr + L.hcbr_words;
+  L.pay_base = o; o += payload_cap * L.pay_words;
+  L.total_words = o;
+  return L;
+}
+
+// Everything the kernel needs that is uniform over the launch.
+struct Params {
+  Layout L;
+  uint32_t num_instances;
+  int32_t max_clock;
+  uint32_t delay_kind;      // LBFT_DELAY_*
+  uint32_t delay_const;     // 1: sigma == 0, the LogNormal value exp(mu) was evaluated on the host
+  int64_t delay_const_value;
+  double mu, sigma;
+  uint64_t uni_lo, uni_span;  // uniform: lo + gen_range(0..span)
+  int32_t tci;                // NodeConfig.target_commit_interval (clamped to 2^30)
+  uint32_t commands_per_epoch;
+  uint32_t quorum;            // EpochConfiguration::quorum_threshold
+  uint64_t silent_mask;
+  uint32_t part_max_len;
+  uint32_t pad0;
+  double zig_r;
+  // device pointers
+  const uint64_t* seeds;      // [num_instances]
+  const double* zig_x;        // [257]
+  const double* zig_f;        // [257]
+  const uint8_t* leader;      // [round_cap + 1] PacemakerState::leader(round), host-evaluated
+  const int32_t* duration;    // [round_cap + 1] (delta * n^gamma) as i64, clamped to 2^30
+  const int32_t* period;      // [round_cap + 1] (lambda * duration) as i64
+  const uint32_t* weights;    // [num_nodes]
+  uint32_t* state;            // tiles
+  // outputs
+  uint32_t* out_commit_counts;  // [I * N]
+  uint32_t* out_lc_round;       // [I * N] round of the last committed block per node
+  uint64_t* out_last_state;     // [I * N]
+  uint32_t* out_counters;       // [I * 12] lbft_instance_counters
+  uint32_t* out_status;         // [I]
+};
+
+}  // namespace lbft

@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's simulator interface over the C ABI.
+
+Reference surface being mirrored (novifinancial/librabft_simulator):
+
+* ``bft_lib::simulator::RandomDelay::new(mean, variance)``                     simulator.rs:99-106
+* ``librabft_v2::node::NodeConfig {target_commit_interval, delta, gamma, lambda}``  node.rs:76-81
+* ``bft_lib::simulator::Simulator::new(seed, num_nodes, delay, context_factory)``   simulator.rs:200-208
+* ``Simulator::loop_until(GlobalTime(max_clock), csv_path) -> Vec<&Context>``       simulator.rs:380
+* ``SimulatedContext::committed_history()`` / ``last_committed_state()``            simulated_context.rs:98-100,194-196
+
+``BatchSimulator`` is the batched form (one handle = many independent ``Simulator`` instances, one per seed,
+advanced in lockstep on one B200); ``Simulator`` is the single-instance spelling of the reference.  All the
+simulation work happens in the CUDA library; this module only marshals arguments and results.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+DELAY_LOGNORMAL, DELAY_UNIFORM = 0, 1
+
+
+@dataclass(frozen=True)
+class RandomDelay:
+    """``RandomDelay`` (simulator.rs:39-43).  ``new`` is the reference's LogNormal; ``uniform`` is an extension."""
+    kind: int = DELAY_LOGNORMAL
+    mean: float = 10.0
+    variance: float = 4.0
+    lo: int = 0
+    hi: int = 0
+
+    @staticmethod
+    def new(mean, variance):
+        return RandomDelay(DELAY_LOGNORMAL, float(mean), float(variance))
+
+    @staticmethod
+    def uniform(lo, hi):
+        return RandomDelay(DELAY_UNIFORM, 0.0, 0.0, int(lo), int(hi))
+
+
+@dataclass(frozen=True)
+class NodeConfig:
+    """``NodeConfig`` (node.rs:76-81) with the CLI defaults of main.rs:72-172."""
+    target_commit_interval: int = 100000
+    delta: int = 20
+    gamma: float = 2.0
+    lambda_: float = 0.5
+
+
+@dataclass(frozen=True)
+class GlobalTime:
+    """``GlobalTime(i64)`` (simulator.rs:35-37)."""
+    value: int
+
+    def __int__(self):
+        return int(self.value)
+
+
+@dataclass(frozen=True)
+class Command:
+    """``Command {proposer, index}`` (simulated_context.rs:31-35)."""
+    proposer: int
+    index: int
+
+
+class SimulatedContextView:
+    """Read-only view of one node's ``SimulatedContext`` after the run (simulated_context.rs:74-100)."""
+
+    def __init__(self, batch, instance, author):
+        self._batch, self._instance, self.author = batch, instance, author
+
+    def committed_history(self):
+        """``committed_history()`` -> list of ``(Command, NodeTime)`` (simulated_context.rs:98-100)."""
+        return [(Command(p, i), t) for (p, i, t) in self._batch.commit_log(self._instance, self.author)]
+
+    def last_committed_state(self):
+        """``StateFinalizer::last_committed_state()`` -> the ``State(u64)`` key (simulated_context.rs:194-196)."""
+        return int(self._batch.last_committed_states[self._instance, self.author])
+
+    def num_commits(self):
+        return int(self._batch.commit_counts[self._instance, self.author])
+
+
+class BatchResult:
+    """Results of ``BatchSimulator.loop_until``: what the reference's callers read from ``Vec<&Context>``."""
+
+    def __init__(self, sim):
+        self._sim = sim
+        self.commit_counts = sim._fetch_u32("lbft_commit_counts", (sim.num_instances, sim.num_nodes))
+        self.last_committed_states = sim._fetch_u64("lbft_last_states", (sim.num_instances, sim.num_nodes))
+        self.counters = sim._fetch_u32("lbft_counters", (sim.num_instances, 12))
+        self.status = sim._fetch_u32("lbft_status", (sim.num_instances,))
+
+    # lbft_instance_counters columns
+    @property
+    def events_processed(self):
+        return self.counters[:, 0:4].sum(axis=1)
+
+    @property
+    def active_rounds(self):
+        """max over nodes of ``ActiveRound::active_round()`` per instance (simulator.rs:86-88)."""
+        return self.counters[:, 6]
+
+    def commit_log(self, instance, author):
+        return self._sim.commit_log(instance, author)
+
+    def contexts(self, instance=0):
+        """The ``Vec<&Context>`` that ``loop_until`` returns for one instance."""
+        return [SimulatedContextView(self, instance, a) for a in range(self._sim.num_nodes)]
+
+
+class BatchSimulator:
+    """Many independent ``Simulator`` instances (one per seed) on one GPU."""
+
+    def __init__(self, seeds, num_nodes, network_delay=RandomDelay(), node_config=NodeConfig(),
+                 commands_per_epoch=30000, voting_rights=None, silent=None, partition_windows=0,
+                 partition_max_len=0, device=0, round_cap=0, queue_cap=0, payload_cap=0):
+        self._lib = _lib.load()
+        self.seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
+        self.num_instances = int(self.seeds.shape[0])
+        self.num_nodes = int(num_nodes)
+        self.network_delay, self.node_config = network_delay, node_config
+        self.commands_per_epoch = int(commands_per_epoch)
+        self.voting_rights = None if voting_rights is None else np.ascontiguousarray(voting_rights, dtype=np.uint64)
+        self.silent = None if silent is None else np.ascontiguousarray(silent, dtype=np.uint8)
+        self.partition_windows, self.partition_max_len = int(partition_windows), int(partition_max_len)
+        self.device, self.round_cap, self.queue_cap, self.payload_cap = int(device), int(round_cap), int(queue_cap), int(payload_cap)
+        self._handle = None
+        self.timing = None
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def make_config(self, max_clock):
+        c = _lib.LbftConfig()
+        c.struct_size = ctypes.sizeof(_lib.LbftConfig)
+        c.num_instances, c.num_nodes = self.num_instances, self.num_nodes
+        c.delay_kind = self.network_delay.kind
+        c.seeds = self.seeds.ctypes.data
+        c.max_clock = int(max_clock)
+        c.delay_mean, c.delay_variance = self.network_delay.mean, self.network_delay.variance
+        c.delay_lo, c.delay_hi = self.network_delay.lo, self.network_delay.hi
+        c.target_commit_interval, c.delta = self.node_config.target_commit_interval, self.node_config.delta
+        c.gamma, c.lambda_ = self.node_config.gamma, self.node_config.lambda_
+        c.commands_per_epoch = self.commands_per_epoch
+        c.voting_rights = None if self.voting_rights is None else self.voting_rights.ctypes.data
+        c.silent = None if self.silent is None else self.silent.ctypes.data
+        c.partition_windows, c.partition_max_len = self.partition_windows, self.partition_max_len
+        c.device, c.round_cap, c.queue_cap, c.payload_cap = self.device, self.round_cap, self.queue_cap, self.payload_cap
+        return c
+
+    def create(self, max_clock):
+        """``lbft_create``: validate, build the host tables, allocate device state."""
+        self.close()
+        handle = ctypes.c_void_p()
+        cfg = self.make_config(max_clock)
+        _lib.check(self._lib.lbft_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._handle = handle
+        return self
+
+    def close(self):
+        if self._handle is not None:
+            self._lib.lbft_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- running --------------------------------------------------------------------------------
+    def loop_until(self, max_clock, csv_path=None, strict=True):
+        """``Simulator::new`` + ``loop_until(max_clock)`` for every instance; host buffers in, host results out."""
+        if csv_path is not None:
+            raise NotImplementedError("DataWriter CSV output (data_writer.rs) is not part of the accelerated path")
+        self.create(int(max_clock))
+        code = self._lib.lbft_run(self._handle)
+        _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
+        self._read_timing()
+        return BatchResult(self)
+
+    def set_seeds(self, seeds):
+        """Re-seed the batch: the next run is a fresh ``Simulator::new(seed, ..)`` per instance."""
+        seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
+        if seeds.shape[0] != self.num_instances:
+            raise ValueError("expected %d seeds" % self.num_instances)
+        self.seeds = seeds
+        _lib.check(self._lib.lbft_set_seeds(self._handle, ctypes.c_void_p(seeds.ctypes.data)))
+
+    def run(self, strict=True):
+        """``lbft_run`` on the existing handle: seeds host->device, event-loop kernel, summaries device->host."""
+        code = self._lib.lbft_run(self._handle)
+        _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
+        self._read_timing()
+        return BatchResult(self)
+
+    def device_buffer(self, which):
+        """(device pointer, bytes) of a result buffer: 0 commit counts, 1 last states, 2 counters, 3 status."""
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(self._lib.lbft_device_buffer(self._handle, which, ctypes.byref(ptr), ctypes.byref(nbytes)))
+        return int(ptr.value), int(nbytes.value)
+
+    def upload(self):
+        _lib.check(self._lib.lbft_upload(self._handle))
+
+    def run_device(self):
+        _lib.check(self._lib.lbft_run_device(self._handle))
+        self._read_timing()
+
+    def download(self, strict=True):
+        _lib.check(self._lib.lbft_download(self._handle), allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
+        self._read_timing()
+        return BatchResult(self)
+
+    def _read_timing(self):
+        t = _lib.LbftTiming()
+        _lib.check(self._lib.lbft_timing_info(self._handle, ctypes.byref(t)))
+        self.timing = t
+
+    def memory_info(self):
+        b, w = ctypes.c_uint64(), ctypes.c_uint32()
+        _lib.check(self._lib.lbft_memory_info(self._handle, ctypes.byref(b), ctypes.byref(w)))
+        return int(b.value), int(w.value)
+
+    # -- results --------------------------------------------------------------------------------
+    def _fetch_u32(self, fn, shape):
+        out = np.zeros(shape, dtype=np.uint32)
+        _lib.check(getattr(self._lib, fn)(self._handle, ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def _fetch_u64(self, fn, shape):
+        out = np.zeros(shape, dtype=np.uint64)
+        _lib.check(getattr(self._lib, fn)(self._handle, ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def commit_log(self, instance, author):
+        """``committed_history()`` of one node as a list of ``(proposer, index, time)``."""
+        n = ctypes.c_size_t(0)
+        _lib.check(self._lib.lbft_commit_log(self._handle, instance, author, None, 0, ctypes.byref(n)))
+        buf = (_lib.LbftCommit * max(1, n.value))()
+        _lib.check(self._lib.lbft_commit_log(self._handle, instance, author, buf, n.value, ctypes.byref(n)))
+        return [(int(buf[i].proposer), int(buf[i].index), int(buf[i].time)) for i in range(n.value)]
+
+
+class Simulator:
+    """Single-instance spelling of ``bft_lib::simulator::Simulator`` (simulator.rs:200-208, 380).
+
+    ``context_factory`` is accepted for signature compatibility with the reference's callers
+    (main.rs:23-34, simulated_run.rs:29-42); it may be ``None`` or a ``NodeConfig`` /
+    ``(NodeConfig, commands_per_epoch)`` describing what the reference's closure would build.
+    """
+
+    def __init__(self, rng_seed, num_nodes, network_delay, context_factory=None, **kw):
+        node_config, cpe = NodeConfig(), 30000
+        if isinstance(context_factory, NodeConfig):
+            node_config = context_factory
+        elif isinstance(context_factory, tuple):
+            node_config, cpe = context_factory
+        elif context_factory is not None:
+            raise TypeError("context_factory must be None, a NodeConfig or (NodeConfig, commands_per_epoch)")
+        self._batch = BatchSimulator([rng_seed], num_nodes, network_delay, node_config, cpe, **kw)
+
+    @staticmethod
+    def new(rng_seed, num_nodes, network_delay, context_factory=None, **kw):
+        return Simulator(rng_seed, num_nodes, network_delay, context_factory, **kw)
+
+    def loop_until(self, max_clock, csv_path=None):
+        res = self._batch.loop_until(int(max_clock), csv_path)
+        self.result = res
+        return res.contexts(0)

@@ -1159,6 +1159,7 @@ struct SimCounters {
   uint64_t scheduled[4] = {0, 0, 0, 0};
   uint64_t max_queue = 0;
   uint64_t dropped_partition = 0;
+  uint64_t scheduled_notify = 0;  // Notify events handed a creation stamp (incl. partition-dropped)
 };
 
 struct Simulator {
@@ -1261,6 +1262,7 @@ struct Simulator {
     if (!receivers.empty()) {  // create_notification has no side effect; only materialise when sent
       int p = (int)notif_pool.size();
       notif_pool.push_back(node.node.create_notification(node.context));
+      counters.scheduled_notify += receivers.size();
       for (Author r : receivers) schedule_network_event(EV_NOTIFY, r, author, p);
     }
     std::vector<Author> senders;

@@ -80,6 +80,7 @@ static void run_one(const lbft_config* c, const SimConfig& base, uint32_t inst, 
     k.max_active_round = (uint32_t)sim.max_active_round();
     k.rng_draws = (uint32_t)sim.rng.draws;
     k.max_queue = (uint32_t)sim.counters.max_queue;
+    k.scheduled_notify = (uint32_t)sim.counters.scheduled_notify;
   }
   if (status) status[inst] = st;
 }

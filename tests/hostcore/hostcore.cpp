@@ -1,0 +1,58 @@
+// hostcore.cpp — TEST INFRASTRUCTURE: compiles the device state machine (csrc/sim_core.cuh) with g++
+// so that its logic can be checked against the oracle in the CPU-only container.  It is never part
+// of, linked into, or reachable from the product library (librabft_simulator_b200/csrc/liblbft_b200.so).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../librabft_simulator_b200/csrc/host_setup.hpp"
+#include "../../librabft_simulator_b200/csrc/sim_core.cuh"
+
+using namespace lbft;
+static thread_local std::string g_err;
+
+template <int NMAX>
+static void run_all(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
+  for (uint32_t inst = 0; inst < P.num_instances; inst++) {
+    uint32_t tile = inst / 32, lane = inst % 32;
+    TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32 + lane};
+    Core<TileMem<32>, NMAX> core(P, mem, zx, zf);
+    core.init(P.seeds[inst]);
+    core.run();
+    core.finalize(inst);
+  }
+}
+
+extern "C" {
+const char* hostcore_last_error(void) { return g_err.c_str(); }
+
+// Same outputs as the product's lbft_* getters; chain_out (optional) receives, per instance,
+// round_cap * 2 words of the chain table and leader_out (optional) the leader table.
+int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
+                 uint32_t* counters, uint32_t* status, uint32_t* words_per_instance) {
+  HostSetup hs;
+  if (!hs.build(*c)) { g_err = hs.error; return LBFT_ERR_INVALID; }
+  Params P = hs.params;
+  P.seeds = c->seeds;
+  P.zig_x = hs.zig_x.data();
+  P.zig_f = hs.zig_f.data();
+  P.leader = hs.leader.data();
+  P.duration = hs.duration.data();
+  P.period = hs.period.data();
+  P.weights = hs.weights.data();
+  uint32_t tiles = (c->num_instances + 31) / 32;
+  std::vector<uint32_t> state((size_t)tiles * P.L.total_words * 32, 0xdeadbeefu);
+  P.state = state.data();
+  P.out_commit_counts = commit_counts;
+  P.out_last_state = last_states;
+  P.out_lc_round = lc_round;
+  P.out_counters = counters;
+  P.out_status = status;
+  if (words_per_instance) *words_per_instance = P.L.total_words;
+  if (c->num_nodes <= 16) run_all<16>(P, state, P.zig_x, P.zig_f);
+  else if (c->num_nodes <= 32) run_all<32>(P, state, P.zig_x, P.zig_f);
+  else run_all<64>(P, state, P.zig_x, P.zig_f);
+  return LBFT_OK;
+}
+}

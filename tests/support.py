@@ -1,0 +1,144 @@
+"""Test support: ctypes wrappers of the ORACLE (oracle/liblbft_oracle.so) and of the host-compiled
+device core (tests/hostcore/libhostcore.so).  Both are test infrastructure; nothing here is imported
+by the product package."""
+import ctypes
+import os
+
+import numpy as np
+
+from librabft_simulator_b200 import _build
+from librabft_simulator_b200._lib import LbftCommit, LbftConfig
+
+P = ctypes.c_void_p
+
+# Reference defaults: librabft-v2/tests/simulated_run.rs:29-42 == main.rs:72-172
+REF = dict(delay_mean=10.0, delay_variance=4.0, target_commit_interval=100000, delta=20, gamma=2.0,
+           lambda_=0.5, commands_per_epoch=30000)
+
+
+def make_config(seeds, num_nodes, max_clock=1000, **kw):
+    """Build an lbft_config; returns (config, keepalive) — keepalive owns the arrays it points to."""
+    seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
+    c = LbftConfig()
+    c.struct_size = ctypes.sizeof(LbftConfig)
+    c.num_instances, c.num_nodes, c.delay_kind = len(seeds), num_nodes, 0
+    c.seeds = seeds.ctypes.data
+    c.max_clock = max_clock
+    keep = [seeds]
+    vals = dict(REF)
+    vals.update(kw)
+    for k, v in vals.items():
+        if k in ("voting_rights", "silent"):
+            if v is None:
+                continue
+            arr = np.ascontiguousarray(v, dtype=np.uint64 if k == "voting_rights" else np.uint8)
+            keep.append(arr)
+            setattr(c, k, arr.ctypes.data)
+        else:
+            setattr(c, k, v)
+    return c, keep
+
+
+class Result:
+    def __init__(self, I, N):
+        self.commit_counts = np.zeros((I, N), np.uint32)
+        self.last_states = np.zeros((I, N), np.uint64)
+        self.counters = np.zeros((I, 12), np.uint32)
+        self.status = np.zeros(I, np.uint32)
+        self.seconds = 0.0
+
+
+class Oracle:
+    def __init__(self):
+        path = _build.build_oracle()
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.lbfo_last_error.restype = ctypes.c_char_p
+        L.lbfo_siphash13.restype = ctypes.c_uint64
+        L.lbfo_siphash13.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        L.lbfo_state_key.restype = ctypes.c_uint64
+        L.lbfo_state_key.argtypes = [ctypes.POINTER(LbftCommit), ctypes.c_size_t]
+        L.lbfo_run_batch.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, P, P, P, P,
+                                     ctypes.POINTER(ctypes.c_double)]
+        L.lbfo_commit_log.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(LbftCommit),
+                                      ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.lbfo_xoshiro_seq.argtypes = [ctypes.c_uint64, P, ctypes.c_size_t]
+        L.lbfo_pick_author.argtypes = [P, ctypes.c_uint32, ctypes.c_uint64]
+        L.lbfo_pick_author.restype = ctypes.c_uint32
+        L.lbfo_leader.argtypes = [P, ctypes.c_uint32, ctypes.c_uint64]
+        L.lbfo_leader.restype = ctypes.c_uint32
+        L.lbfo_quorum_threshold.argtypes = [P, ctypes.c_uint32]
+        L.lbfo_quorum_threshold.restype = ctypes.c_uint64
+        L.lbfo_ziggurat_tables.argtypes = [P, P]
+        L.lbfo_delay_samples.argtypes = [ctypes.c_uint64, ctypes.c_double, ctypes.c_double, P, ctypes.c_size_t]
+        L.lbfo_normal_samples.argtypes = [ctypes.c_uint64, P, ctypes.c_size_t]
+        L.lbfo_shuffle.argtypes = [ctypes.c_uint64, P, ctypes.c_size_t]
+        L.lbfo_round_durations.argtypes = [ctypes.c_int64, ctypes.c_double, ctypes.c_double, P, P, ctypes.c_size_t]
+        L.lbfo_selftest.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+
+    def run(self, seeds, num_nodes, max_clock=1000, threads=0, first=0, count=None, **kw):
+        cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
+        I = cfg.num_instances
+        count = I - first if count is None else count
+        res = Result(I, num_nodes)
+        sec = ctypes.c_double()
+        threads = threads or (os.cpu_count() or 1)
+        rc = self.lib.lbfo_run_batch(ctypes.byref(cfg), first, count, threads, P(res.commit_counts.ctypes.data),
+                                     P(res.last_states.ctypes.data), P(res.counters.ctypes.data),
+                                     P(res.status.ctypes.data), ctypes.byref(sec))
+        if rc != 0:
+            raise RuntimeError(self.lib.lbfo_last_error().decode())
+        res.seconds = sec.value
+        return res
+
+    def commit_log(self, seeds, num_nodes, instance, node, max_clock=1000, **kw):
+        cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
+        n = ctypes.c_size_t()
+        buf = (LbftCommit * 65536)()
+        rc = self.lib.lbfo_commit_log(ctypes.byref(cfg), instance, node, buf, 65536, ctypes.byref(n))
+        if rc != 0:
+            raise RuntimeError(self.lib.lbfo_last_error().decode())
+        return [(int(buf[i].proposer), int(buf[i].index), int(buf[i].time)) for i in range(n.value)]
+
+    def state_key(self, log):
+        buf = (LbftCommit * max(1, len(log)))()
+        for i, (p, idx, t) in enumerate(log):
+            buf[i].proposer, buf[i].index, buf[i].time = p, idx, t
+        return int(self.lib.lbfo_state_key(buf, len(log)))
+
+    def selftest(self):
+        buf = ctypes.create_string_buffer(8192)
+        return self.lib.lbfo_selftest(buf, 8192), buf.value.decode()
+
+
+class HostCore:
+    """The device state machine compiled for the host (CPU-side check of the kernel's logic)."""
+
+    def __init__(self):
+        path = _build.build_hostcore()
+        self.lib = ctypes.CDLL(path)
+        self.lib.hostcore_last_error.restype = ctypes.c_char_p
+        self.lib.hostcore_run.argtypes = [ctypes.POINTER(LbftConfig), P, P, P, P, P, ctypes.POINTER(ctypes.c_uint32)]
+
+    def run(self, seeds, num_nodes, max_clock=1000, **kw):
+        cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
+        I = cfg.num_instances
+        res = Result(I, num_nodes)
+        res.lc_round = np.zeros((I, num_nodes), np.uint32)
+        w = ctypes.c_uint32()
+        rc = self.lib.hostcore_run(ctypes.byref(cfg), P(res.commit_counts.ctypes.data), P(res.last_states.ctypes.data),
+                                   P(res.lc_round.ctypes.data), P(res.counters.ctypes.data), P(res.status.ctypes.data),
+                                   ctypes.byref(w))
+        if rc != 0:
+            raise RuntimeError(self.lib.hostcore_last_error().decode())
+        res.words_per_instance = w.value
+        return res
+
+
+def assert_same(a, b, what=""):
+    """Bit-exact comparison of two Result objects on everything the reference exposes."""
+    np.testing.assert_array_equal(a.commit_counts, b.commit_counts, err_msg="commit counts differ " + what)
+    np.testing.assert_array_equal(a.last_states, b.last_states, err_msg="last committed states differ " + what)
+    # processed-by-kind, cancelled timers, creation stamps, max active round, RNG draws
+    np.testing.assert_array_equal(a.counters[:, :8], b.counters[:, :8], err_msg="event counters differ " + what)
+    np.testing.assert_array_equal(a.counters[:, 9], b.counters[:, 9], err_msg="scheduled notifications differ " + what)

@@ -1,0 +1,79 @@
+"""The product's C-ABI library loads and exports every symbol include/lbft.h declares; argument validation
+works without a GPU; and there is NO CPU fallback (creating a simulator without a device fails loudly)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from librabft_simulator_b200 import _build, _lib
+from tests.support import make_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build_product()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, "include", "lbft.h")).read()
+    declared = set(re.findall(r"\b(lbft_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_abi_version_and_struct_size(lib):
+    assert lib.lbft_abi_version() == 1
+    assert ctypes.sizeof(_lib.LbftConfig) == 152
+    assert ctypes.sizeof(_lib.LbftCommit) == 16
+
+
+def test_invalid_configs_are_rejected(lib):
+    h = ctypes.c_void_p()
+    cfg, keep = make_config([1, 2], 4)
+    cfg.struct_size = 12
+    assert lib.lbft_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"struct_size" in lib.lbft_last_error()
+    for field, value in (("num_nodes", 0), ("num_nodes", 65), ("max_clock", -1), ("delay_kind", 7), ("flags", 1),
+                         ("commands_per_epoch", 0), ("delay_mean", -1.0)):
+        cfg, keep = make_config([1, 2], 4)
+        setattr(cfg, field, value)
+        assert lib.lbft_create(ctypes.byref(cfg), ctypes.byref(h)) == -1, field
+        assert h.value is None
+    assert lib.lbft_create(None, ctypes.byref(h)) == -1
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    h = ctypes.c_void_p()
+    cfg, keep = make_config([1, 2, 3], 4)
+    rc = lib.lbft_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == -2, "without a GPU the product must fail with LBFT_ERR_CUDA, not fall back to the CPU"
+    assert b"no CPU fallback" in lib.lbft_last_error()
+
+
+def test_product_does_not_link_the_oracle():
+    # the product sources never #include / import anything from oracle/ or tests/
+    pkg = os.path.join(ROOT, "librabft_simulator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".cu", ".cuh", ".h", ".hpp", ".py")):
+                continue
+            for line in open(os.path.join(dirpath, f)):
+                t = line.strip()
+                if t.startswith("#include"):
+                    assert "oracle" not in t and "tests/" not in t and "hostcore" not in t, (f, t)
+                if f != "_build.py" and (t.startswith("import ") or t.startswith("from ")):
+                    assert "oracle" not in t and "tests" not in t.split(), (f, t)
+    # ... and the shared object does not carry oracle symbols
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", _build.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "lbfo_" not in syms and "lbft_oracle" not in syms and "hostcore" not in syms

@@ -1,0 +1,56 @@
+"""CPU-side check of the DEVICE state machine: csrc/sim_core.cuh compiled with g++ (tests/hostcore) must
+reproduce the oracle bit-for-bit — commit counts, SipHash state keys, events processed by kind, cancelled
+timers, creation stamps, active rounds and RNG draw counts.  This validates the round-id layout and every
+protocol rule of the kernel source before it reaches a GPU."""
+import numpy as np
+import pytest
+
+from tests.support import assert_same
+
+CASES = [
+    # (first seed, instances, nodes, max_clock, extra)
+    (52, 1, 3, 1000, {}),     # golden 1 (simulated_run.rs:45-66)
+    (48, 1, 8, 1000, {}),     # golden 2 (simulated_run.rs:68-94)
+    (1, 96, 4, 1000, {}),     # BASELINE config 2/3 shape
+    (1000, 40, 3, 1000, {}),
+    (5, 24, 7, 1000, {}),     # config 5 shape without partitions
+    (77, 4, 16, 600, {}),
+    (3, 16, 2, 1000, {}),
+    (52, 2, 3, 3000, {"delay_variance": 0.0}),  # config 1: fixed 10 ms, >100 rounds
+    (11, 16, 4, 2500, {}),    # longer horizon
+    (21, 16, 4, 1000, {"delay_mean": 25.0, "delay_variance": 200.0}),  # heavy jitter -> timeouts/TCs
+    (31, 16, 5, 1500, {"delta": 5, "gamma": 1.5, "lambda_": 0.25, "queue_cap": 4096, "payload_cap": 1024}),   # tight pacemaker -> many timeouts, query-all
+    (41, 8, 4, 4000, {"target_commit_interval": 300, "delta": 400}),  # commit tracker query-all path
+]
+
+
+@pytest.mark.parametrize("seed0,count,nodes,max_clock,extra", CASES)
+def test_hostcore_matches_oracle(oracle, hostcore, seed0, count, nodes, max_clock, extra):
+    seeds = np.arange(seed0, seed0 + count, dtype=np.uint64)
+    o = oracle.run(seeds, nodes, max_clock, **extra)
+    h = hostcore.run(seeds, nodes, max_clock, **extra)
+    assert (o.status == 1).all()
+    assert ((h.status & ~np.uint32(64)) == 1).all(), h.status
+    assert_same(o, h, "N=%d" % nodes)
+
+
+def test_goldens_through_hostcore(hostcore):
+    r = hostcore.run([52], 3, 1000)
+    assert r.commit_counts.tolist() == [[27, 27, 27]]
+    assert r.last_states.tolist() == [[11134312813757838303] * 3]
+    r = hostcore.run([48], 8, 1000)
+    assert r.commit_counts.tolist() == [[28] * 7 + [30]]
+    assert r.last_states.tolist() == [[12785928431398617538] * 7 + [4890275890002623733]]
+
+
+def test_round_overflow_is_flagged(hostcore):
+    # a single node makes a round per millisecond: the default round_cap cannot hold 1000 rounds
+    r = hostcore.run([3], 1, 1000)
+    assert r.status[0] & 2
+    r = hostcore.run([3], 1, 1000, round_cap=1056)
+    assert r.status[0] == 1 and r.commit_counts[0, 0] > 900
+
+
+def test_queue_overflow_is_flagged(hostcore):
+    r = hostcore.run([9], 8, 1000, queue_cap=16, round_cap=0)
+    assert r.status[0] & (4 | 2 | 8)
