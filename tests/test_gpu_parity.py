@@ -108,3 +108,30 @@ def test_capacity_overflow_is_reported_not_hidden():
     assert e.value.code == _lib.LBFT_ERR_CAPACITY
     sim, g = gpu_run([9, 10], 8, 1000, strict=False, queue_cap=32, round_cap=32)
     assert (g.status & _lib.ST_ERROR_MASK).all()
+
+
+# ---- BASELINE configs 2, 4, 5: extension features (semantics fixed by the oracle) ----
+W64 = [1 + (i % 3) for i in range(64)]
+SILENT64 = [1 if i % 3 == 0 and i <= 60 else 0 for i in range(64)]
+
+EXT_CASES = [
+    ("config2_uniform_delay", 1, 1024, 4, 1000, {"delay_kind": 1, "delay_lo": 5, "delay_hi": 15}),
+    ("weighted", 7, 32, 5, 1000, {"voting_rights": [1, 2, 5, 1, 3]}),
+    ("silent_f1", 100, 32, 4, 2000, {"silent": [0, 0, 0, 1]}),
+    ("silent_no_quorum", 100, 8, 4, 1000, {"silent": [0, 1, 1, 0]}),
+    ("config4_64_authors_weighted_silent", 1, 4, 64, 400, {"voting_rights": W64, "silent": SILENT64}),
+    ("n33", 5, 3, 33, 300, {}),
+    ("config5_partitions", 1000, 96, 7, 1000, {"partition_windows": 4, "partition_max_len": 150}),
+]
+
+
+@pytest.mark.parametrize("name,seed0,count,nodes,max_clock,extra", EXT_CASES)
+def test_gpu_extensions_match_oracle(oracle, name, seed0, count, nodes, max_clock, extra):
+    seeds = np.arange(seed0, seed0 + count, dtype=np.uint64)
+    o = oracle.run(seeds, nodes, max_clock, **extra)
+    sim, g = gpu_run(seeds, nodes, max_clock, **dict(extra))
+    assert (o.status == 1).all()
+    assert ((g.status & ~np.uint32(64)) == 1).all(), np.unique(g.status)
+    assert_same(o, g, name)
+    assert sim.commit_log(count - 1, nodes - 2 if nodes > 1 else 0) == oracle.commit_log(
+        seeds, nodes, count - 1, nodes - 2 if nodes > 1 else 0, max_clock, **extra)
