@@ -73,7 +73,8 @@ typedef struct lbft_instance_counters {
   uint32_t rng_draws;         /* Xoshiro256** next_u64 calls on the instance stream                    */
   uint32_t max_queue;         /* high-water mark of the device event queue (implementation-specific)   */
   uint32_t scheduled_notify;  /* DataSyncNotifyEvents handed a creation stamp (simulator.rs:348-354)    */
-  uint32_t reserved[2];
+  uint32_t max_payloads;      /* high-water mark of in-flight notification snapshots (implementation)   */
+  uint32_t reserved;
 } lbft_instance_counters;
 
 /* Device timing of the last lbft_run / lbft_run_device, measured with CUDA events on the stream the

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -77,6 +78,7 @@ struct HostSetup {
   std::vector<uint8_t> leader;
   std::vector<int32_t> duration, period;
   std::vector<uint32_t> weights;
+  std::vector<double> delay_thr;  // see build_delay_table()
   std::string error;
 
   bool build(const lbft_config& c) {
@@ -131,12 +133,18 @@ struct HostSetup {
     rcap = (rcap + 31) / 32 * 32;
     if (rcap < 32) rcap = 32;
     if (rcap > 32768) return fail("round_cap must be <= 32768");
-    uint32_t qcap = c.queue_cap ? c.queue_cap : pow2_ceil(6 * N * N + 32);
-    if (qcap < rcap) qcap = rcap;  // the read-out kernel reuses the queue area as chain scratch
+    // Small committees use the scan queue (64-bit entries: time:24 | 3-kind:2 | stamp:22 | slot:8 | sender:4 |
+    // receiver:4, O(1) append, linear min-scan); larger ones the binary heap with 3-word entries.
+    // (explicit capacities beyond what the scan queue can encode / scan efficiently select the heap.)
+    uint32_t qscan = (N <= 5 && c.max_clock < (1 << 24) - 64) ? 1u : 0u;
+    if (c.payload_cap > 255 || c.queue_cap > 512) qscan = 0;
+    uint32_t qcap = c.queue_cap ? c.queue_cap : (qscan ? (N <= 4 ? 64u : 8 * N * N) : pow2_ceil(6 * N * N + 32));
+    if (2 * qcap < rcap && qscan) qcap = (rcap + 1) / 2;  // the read-out reuses the queue area as chain scratch
+    if (qcap < rcap && !qscan) qcap = rcap;
     if (qcap > (1u << 20)) return fail("queue_cap too large");
-    uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 8 ? 64 : pow2_ceil(N * N));
+    uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 4 ? 32u : (N <= 8 ? 64u : pow2_ceil(N * N)));
     if (pcap > 0xfff0u) return fail("payload_cap must be < 65520");
-    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows);
+    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan);
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
     leader.resize(rcap + 1);
     for (uint32_t r = 0; r <= rcap; r++) leader[r] = (uint8_t)pick_author(weights, total, siphash13_u64(r));
@@ -153,7 +161,47 @@ struct HostSetup {
       period[n] = (int32_t)(per > CL ? CL : (per < -CL ? -CL : per));
     }
     build_ziggurat();
+    build_delay_table();
     return true;
+  }
+
+  // LogNormal delay without a device-side exp(): the reference truncates exp(mu + sigma*z) to an integer
+  // (simulator.rs:115-117), so only the integer part matters.  delay_thr[k] is the smallest double z with
+  // (exp(mu + sigma*z) as i64) >= k, found by bisection over the doubles with the HOST libm — the very
+  // function the Rust reference calls — so the device result is bit-identical to the host's by
+  // construction (no last-ulp dependence on the CUDA math library).  Table: thr[0] = -inf,
+  // thr[1..kmax], thr[kmax+1] = +inf, where kmax = delay at the largest deviate the ziggurat can emit.
+  void build_delay_table() {
+    Params& p = params;
+    p.delay_kmax = 0;
+    delay_thr.clear();
+    if (p.delay_kind != LBFT_DELAY_LOGNORMAL || p.delay_const) return;
+    const double mu = p.mu, sigma = p.sigma;
+    auto D = [mu, sigma](double z) -> int64_t {
+      double v = std::exp(mu + sigma * z);
+      return v >= 9.0e18 ? INT64_MAX : (int64_t)v;
+    };
+    const double ZMAX = 14.0;  // |z| <= R + 52*ln(2)/R ~ 13.52 for the 256-layer ziggurat with 52-bit uniforms
+    int64_t kmax = D(ZMAX);
+    if (kmax < 1 || kmax > 4096) return;  // too wide: keep the exp() path
+    auto key = [](double d) { int64_t b; memcpy(&b, &d, 8); return b < 0 ? INT64_MIN - b : b; };  // monotone map
+    auto unkey = [](int64_t k) { int64_t b = k < 0 ? INT64_MIN - k : k; double d; memcpy(&d, &b, 8); return d; };
+    delay_thr.assign((size_t)kmax + 2, 0.0);
+    delay_thr[0] = -INFINITY;
+    delay_thr[kmax + 1] = INFINITY;
+    for (int64_t k = 1; k <= kmax; k++) {
+      if (D(-ZMAX) >= k) { delay_thr[k] = -INFINITY; continue; }
+      int64_t lo = key(-ZMAX), hi = key(ZMAX);  // D(lo) < k <= D(hi)
+      while (hi - lo > 1) {
+        int64_t mid = lo + (hi - lo) / 2;
+        if (D(unkey(mid)) >= k) hi = mid; else lo = mid;
+      }
+      delay_thr[k] = unkey(hi);
+      // exp() must be monotone across the threshold for the table to be exact: check a few ulps either side
+      for (int j = 1; j <= 4; j++)
+        if (D(unkey(hi + j)) < k || D(unkey(hi - j)) >= k) { delay_thr.clear(); return; }
+    }
+    p.delay_kmax = (uint32_t)kmax;
   }
 
   // rand_distr 0.4.0 ziggurat_tables.rs (ZIG_NORM_X / ZIG_NORM_F / ZIG_NORM_R): regenerated with the

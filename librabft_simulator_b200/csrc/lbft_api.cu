@@ -34,7 +34,7 @@ static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter 
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 32;
 
-template <int NMAX>
+template <int NMAX, bool QSCAN>
 __global__ void __launch_bounds__(kBlockThreads) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   __shared__ double s_zx[257];
   __shared__ double s_zf[257];
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(kBlockThreads) lbft_event_loop_kernel(const __
   const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= P.num_instances) return;
   const uint32_t tile = inst >> 5, lane = inst & 31;
-  TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32 + lane};
-  Core<TileMem<32>, NMAX> core(P, mem, s_zx, s_zf);
+  TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32, lane};
+  Core<TileMem<32>, NMAX, QSCAN> core(P, mem, s_zx, s_zf);
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
@@ -84,6 +84,7 @@ struct lbft_sim {
   int32_t* d_duration = nullptr;
   int32_t* d_period = nullptr;
   uint32_t* d_weights = nullptr;
+  double* d_delay_thr = nullptr;
   uint32_t* d_state = nullptr;
   uint32_t* d_commit_counts = nullptr;
   uint32_t* d_lc_round = nullptr;
@@ -113,7 +114,7 @@ static void free_all(lbft_sim* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaFree(s->d_seeds); cudaFree(s->d_zx); cudaFree(s->d_zf); cudaFree(s->d_leader); cudaFree(s->d_duration);
-  cudaFree(s->d_period); cudaFree(s->d_weights); cudaFree(s->d_state); cudaFree(s->d_commit_counts);
+  cudaFree(s->d_period); cudaFree(s->d_weights); cudaFree(s->d_delay_thr); cudaFree(s->d_state); cudaFree(s->d_commit_counts);
   cudaFree(s->d_lc_round); cudaFree(s->d_last_state); cudaFree(s->d_counters); cudaFree(s->d_status);
   cudaFreeHost(s->h_seeds); cudaFreeHost(s->h_commit_counts); cudaFreeHost(s->h_lc_round);
   cudaFreeHost(s->h_last_state); cudaFreeHost(s->h_counters); cudaFreeHost(s->h_status);
@@ -173,6 +174,7 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
   CREATE_TRY(dev_alloc(s, &s->d_duration, L.round_cap + 1));
   CREATE_TRY(dev_alloc(s, &s->d_period, L.round_cap + 1));
   CREATE_TRY(dev_alloc(s, &s->d_weights, N));
+  if (!s->hs.delay_thr.empty()) CREATE_TRY(dev_alloc(s, &s->d_delay_thr, s->hs.delay_thr.size()));
   CREATE_TRY(dev_alloc(s, &s->d_state, tiles * L.total_words * 32));
   CREATE_TRY(dev_alloc(s, &s->d_commit_counts, I * N));
   CREATE_TRY(dev_alloc(s, &s->d_lc_round, I * N));
@@ -193,6 +195,8 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
   CREATE_TRY(cudaMemcpy(s->d_duration, s->hs.duration.data(), (L.round_cap + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
   CREATE_TRY(cudaMemcpy(s->d_period, s->hs.period.data(), (L.round_cap + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
   CREATE_TRY(cudaMemcpy(s->d_weights, s->hs.weights.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (s->d_delay_thr)
+    CREATE_TRY(cudaMemcpy(s->d_delay_thr, s->hs.delay_thr.data(), s->hs.delay_thr.size() * sizeof(double), cudaMemcpyHostToDevice));
 #undef CREATE_TRY
   s->P = s->hs.params;
   s->P.seeds = s->d_seeds;
@@ -202,6 +206,7 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
   s->P.duration = s->d_duration;
   s->P.period = s->d_period;
   s->P.weights = s->d_weights;
+  s->P.delay_thr = s->d_delay_thr;
   s->P.state = s->d_state;
   s->P.out_commit_counts = s->d_commit_counts;
   s->P.out_lc_round = s->d_lc_round;
@@ -253,9 +258,10 @@ int lbft_run_device(lbft_sim* s) {
   CUDA_TRY(cudaSetDevice(s->device));
   const uint32_t blocks = (s->I + kBlockThreads - 1) / kBlockThreads;
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
-  if (s->N <= 16) lbft_event_loop_kernel<16><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
-  else if (s->N <= 32) lbft_event_loop_kernel<32><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
-  else lbft_event_loop_kernel<64><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  if (s->P.L.queue_scan) lbft_event_loop_kernel<16, true><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  else if (s->N <= 16) lbft_event_loop_kernel<16, false><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  else if (s->N <= 32) lbft_event_loop_kernel<32, false><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  else lbft_event_loop_kernel<64, false><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));

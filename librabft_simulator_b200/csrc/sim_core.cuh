@@ -128,12 +128,22 @@ struct SipWords {
   }
 };
 
-// Strided view of one instance's words inside its warp tile.
+// View of one instance's words inside its warp tile (sim_params.h).  32-bit words are interleaved by lane
+// (word w -> tile[w*STRIDE + lane]); the scan queue's 64-bit entries are interleaved at 8-byte granularity
+// (entry j of the region starting at word wbase -> tile[wbase*STRIDE + j*2*STRIDE + lane*2 .. +1]), so a warp
+// reading entry j issues one 256-byte coalesced access.
 template <int STRIDE>
 struct TileMem {
-  uint32_t* base;  // already offset to the instance's lane
-  LBFT_HD uint32_t ld(uint32_t w) const { return base[(size_t)w * STRIDE]; }
-  LBFT_HD void st(uint32_t w, uint32_t v) const { base[(size_t)w * STRIDE] = v; }
+  uint32_t* tile;  // first word of the tile
+  uint32_t lane;
+  LBFT_HD uint32_t ld(uint32_t w) const { return tile[(size_t)w * STRIDE + lane]; }
+  LBFT_HD void st(uint32_t w, uint32_t v) const { tile[(size_t)w * STRIDE + lane] = v; }
+  LBFT_HD uint64_t ld64(uint32_t wbase, uint32_t j) const {
+    return *reinterpret_cast<const uint64_t*>(tile + (size_t)wbase * STRIDE + (size_t)j * 2 * STRIDE + lane * 2);
+  }
+  LBFT_HD void st64(uint32_t wbase, uint32_t j, uint64_t v) const {
+    *reinterpret_cast<uint64_t*>(tile + (size_t)wbase * STRIDE + (size_t)j * 2 * STRIDE + lane * 2) = v;
+  }
 };
 
 // List of authors used for the shuffled fan-out (simulator.rs:326-343, 356-370).
@@ -165,7 +175,7 @@ struct Actions {  // NodeUpdateActions, interfaces.rs:12-21 (should_send holds a
   bool broadcast, query_all;
 };
 
-template <class Mem, int NMAX>
+template <class Mem, int NMAX, bool QSCAN>
 struct Core {
   const Params& P;
   const Layout& L;
@@ -255,6 +265,17 @@ struct Core {
     if (P.delay_kind == 1u) return (int32_t)(P.uni_lo + gen_range_u64(P.uni_span));
     double z = standard_normal();
     if (P.delay_const) return (int32_t)P.delay_const_value;  // sigma == 0: exp(mu) evaluated by the host libm
+    if (P.delay_kmax) {
+      // (exp(mu + sigma*z) as i64) == number of thresholds <= z; the thresholds were bisected on the host
+      // with the host libm, so this is exact.  Any starting guess works; the walk fixes it up.
+      float g = expf((float)P.mu + (float)P.sigma * (float)z);
+      int32_t k = g < (float)P.delay_kmax ? (int32_t)g : (int32_t)P.delay_kmax;
+      if (k < 0) k = 0;
+      const double* thr = P.delay_thr;
+      while (z >= thr[k + 1]) k++;
+      while (z < thr[k]) k--;
+      return k;
+    }
     double v = exp(add_rn(P.mu, mul_rn(P.sigma, z)));
     double r = rint(v);
     if (fabs(v - r) < 1e-9 * (r > 1.0 ? r : 1.0)) status |= ST_DELAY_NEAR_INT;
@@ -314,11 +335,22 @@ struct Core {
   }
   // schedule_event (simulator.rs:252-264).  Events beyond max_clock can never be popped before the
   // loop ends (:389-391): they consume their creation stamp and are dropped.  Returns true if queued.
+  // `data` = receiver | sender << 8 | slot << 16.
   LBFT_HD bool push_event(int32_t time, uint32_t kind, uint32_t data) {
     uint32_t st = stamp++;
-    if (stamp >= (1u << 30)) status |= ST_QUEUE_OVERFLOW;
+    if (stamp >= (QSCAN ? (1u << 22) : (1u << 30))) status |= ST_QUEUE_OVERFLOW;
     if (time > P.max_clock) return false;
     if (qsize >= L.queue_cap) { status |= ST_QUEUE_OVERFLOW; return false; }
+    if (QSCAN) {
+      // unsorted array, O(1) append.  key = time:24 | 3-kind:2 | stamp:22 | slot:8 | sender:4 | receiver:4;
+      // stamps are unique, so the payload bits below them never decide a comparison.
+      uint64_t key = ((uint64_t)(uint32_t)time << 40) | ((uint64_t)(3u - kind) << 38) | ((uint64_t)st << 16) |
+                     (uint64_t)(((data >> 16) & 0xffu) << 8) | (uint64_t)(((data >> 8) & 0xfu) << 4) | (uint64_t)(data & 0xfu);
+      m.st64(L.heap_time, qsize, key);
+      qsize++;
+      if (qsize > max_queue) max_queue = qsize;
+      return true;
+    }
     uint32_t klo = ((3u - kind) << 30) | st;
     uint64_t key = ((uint64_t)(uint32_t)time << 32) | klo;
     uint32_t i = qsize++;
@@ -335,6 +367,32 @@ struct Core {
     return true;
   }
   LBFT_HD void pop_event(int32_t& time, uint32_t& kind, uint32_t& data) {
+    if (QSCAN) {
+      // linear min-scan: independent, fully coalesced loads; no data-dependent sift chains
+      uint64_t best = m.ld64(L.heap_time, 0);
+      uint32_t bi = 0;
+      const uint32_t n = qsize;
+      uint32_t j = 1;
+      for (; j + 3 < n; j += 4) {
+        uint64_t k0 = m.ld64(L.heap_time, j), k1 = m.ld64(L.heap_time, j + 1), k2 = m.ld64(L.heap_time, j + 2),
+                 k3 = m.ld64(L.heap_time, j + 3);
+        if (k0 < best) { best = k0; bi = j; }
+        if (k1 < best) { best = k1; bi = j + 1; }
+        if (k2 < best) { best = k2; bi = j + 2; }
+        if (k3 < best) { best = k3; bi = j + 3; }
+      }
+      for (; j < n; j++) {
+        uint64_t k0 = m.ld64(L.heap_time, j);
+        if (k0 < best) { best = k0; bi = j; }
+      }
+      qsize = n - 1;
+      if (bi != n - 1) m.st64(L.heap_time, bi, m.ld64(L.heap_time, n - 1));
+      time = (int32_t)(best >> 40);
+      kind = 3u - ((uint32_t)(best >> 38) & 3u);
+      uint32_t lo = (uint32_t)best & 0xffffu, slot = lo >> 8;
+      data = (lo & 0xfu) | (((lo >> 4) & 0xfu) << 8) | ((slot == 0xffu ? PAY_NONE : slot) << 16);
+      return;
+    }
     time = (int32_t)m.ld(L.heap_time);
     uint32_t klo = m.ld(L.heap_key);
     data = m.ld(L.heap_data);
@@ -862,7 +920,7 @@ struct Core {
     uint32_t* c = P.out_counters + (size_t)inst * 12;
     c[0] = proc0; c[1] = proc1; c[2] = proc2; c[3] = proc3;
     c[4] = cancelled; c[5] = stamp; c[6] = max_round; c[7] = draws; c[8] = max_queue;
-    c[9] = sched_notify; c[10] = 0; c[11] = 0;
+    c[9] = sched_notify; c[10] = pay_next; c[11] = 0;
     P.out_status[inst] = status;
   }
 };

@@ -59,6 +59,7 @@ struct Layout {
   uint32_t hcbr_words;   // ceil(N/2): per-author u16 highest_certified_block_round of a timeout
   uint32_t rset_words;   // round_cap/32: per-round bitsets
   uint32_t round_cap, queue_cap, payload_cap, part_windows;
+  uint32_t queue_scan;   // 1: unsorted array + linear min-scan, 64-bit entries (small N); 0: binary heap, 3-word entries
   // word offsets inside a node block
   uint32_t n_vmask, n_tmask, n_tcmask, n_thcbr, n_tchcbr, n_hasblk, n_hasqc, n_pend, node_words;
   // word offsets inside an instance
@@ -69,8 +70,10 @@ struct Layout {
   uint32_t p_tcmask, p_curmask, p_tchcbr, p_curhcbr;
 };
 
-inline Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows) {
+inline Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
+                          uint32_t queue_scan) {
   Layout L{};
+  L.queue_scan = queue_scan;
   L.num_nodes = N;
   L.mask_words = N > 32 ? 2 : 1;
   L.hcbr_words = (N + 1) / 2;
@@ -95,9 +98,10 @@ inline Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, ui
   L.qcmade_base = o; o += L.rset_words;
   L.chain_base = o; o += 2 * round_cap;  // [2r] prev | cmd<<16, [2r+1] time
   L.part_base = o; o += 4 * part_windows;  // t0, t1, mask lo, mask hi
+  o = (o + 1) & ~1u;  // 64-bit entries of the scan queue need an even word offset
   L.heap_time = o; o += queue_cap;
   L.heap_key = o; o += queue_cap;
-  L.heap_data = o; o += queue_cap;
+  if (!queue_scan) { L.heap_data = o; o += queue_cap; }
   L.p_tcmask = 3;
   L.p_curmask = L.p_tcmask + L.mask_words;
   L.p_tchcbr = L.p_curmask + L.mask_words;
@@ -125,6 +129,8 @@ struct Params {
   uint32_t part_max_len;
   uint32_t pad0;
   double zig_r;
+  uint32_t delay_kmax;       // > 0: delay_thr[k] (k = 0..delay_kmax) is valid and replaces exp() on the device
+  uint32_t pad1;
   // device pointers
   const uint64_t* seeds;      // [num_instances]
   const double* zig_x;        // [257]
@@ -133,6 +139,7 @@ struct Params {
   const int32_t* duration;    // [round_cap + 1] (delta * n^gamma) as i64, clamped to 2^30
   const int32_t* period;      // [round_cap + 1] (lambda * duration) as i64
   const uint32_t* weights;    // [num_nodes]
+  const double* delay_thr;    // [delay_kmax + 1] smallest normal deviate z whose LogNormal delay is >= k (host libm)
   uint32_t* state;            // tiles
   // outputs
   uint32_t* out_commit_counts;  // [I * N]

@@ -12,12 +12,12 @@
 using namespace lbft;
 static thread_local std::string g_err;
 
-template <int NMAX>
+template <int NMAX, bool QSCAN>
 static void run_all(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
-    TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32 + lane};
-    Core<TileMem<32>, NMAX> core(P, mem, zx, zf);
+    TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
+    Core<TileMem<32>, NMAX, QSCAN> core(P, mem, zx, zf);
     core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);
@@ -41,6 +41,7 @@ int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_s
   P.duration = hs.duration.data();
   P.period = hs.period.data();
   P.weights = hs.weights.data();
+  P.delay_thr = hs.delay_thr.empty() ? nullptr : hs.delay_thr.data();
   uint32_t tiles = (c->num_instances + 31) / 32;
   std::vector<uint32_t> state((size_t)tiles * P.L.total_words * 32, 0xdeadbeefu);
   P.state = state.data();
@@ -50,9 +51,10 @@ int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_s
   P.out_counters = counters;
   P.out_status = status;
   if (words_per_instance) *words_per_instance = P.L.total_words;
-  if (c->num_nodes <= 16) run_all<16>(P, state, P.zig_x, P.zig_f);
-  else if (c->num_nodes <= 32) run_all<32>(P, state, P.zig_x, P.zig_f);
-  else run_all<64>(P, state, P.zig_x, P.zig_f);
+  if (P.L.queue_scan) run_all<16, true>(P, state, P.zig_x, P.zig_f);
+  else if (c->num_nodes <= 16) run_all<16, false>(P, state, P.zig_x, P.zig_f);
+  else if (c->num_nodes <= 32) run_all<32, false>(P, state, P.zig_x, P.zig_f);
+  else run_all<64, false>(P, state, P.zig_x, P.zig_f);
   return LBFT_OK;
 }
 }
