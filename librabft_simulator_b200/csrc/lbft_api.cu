@@ -34,7 +34,7 @@ static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter 
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 32;
 
-template <int NMAX, bool QSCAN>
+template <int NMAX, bool QSCAN, int RW>
 __global__ void __launch_bounds__(kBlockThreads) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   __shared__ double s_zx[257];
   __shared__ double s_zf[257];
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kBlockThreads) lbft_event_loop_kernel(const __
   if (inst >= P.num_instances) return;
   const uint32_t tile = inst >> 5, lane = inst & 31;
   TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32, lane};
-  Core<TileMem<32>, NMAX, QSCAN> core(P, mem, s_zx, s_zf);
+  Core<TileMem<32>, NMAX, QSCAN, RW> core(P, mem, s_zx, s_zf);
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
@@ -258,10 +258,17 @@ int lbft_run_device(lbft_sim* s) {
   CUDA_TRY(cudaSetDevice(s->device));
   const uint32_t blocks = (s->I + kBlockThreads - 1) / kBlockThreads;
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
-  if (s->P.L.queue_scan) lbft_event_loop_kernel<16, true><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
-  else if (s->N <= 16) lbft_event_loop_kernel<16, false><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
-  else if (s->N <= 32) lbft_event_loop_kernel<32, false><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
-  else lbft_event_loop_kernel<64, false><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);
+  const bool rw4 = s->P.L.rset_words == 4;  // round bitsets held in registers (round_cap == 128)
+#define LBFT_LAUNCH(NMAX, QS)                                                                          \
+  do {                                                                                                 \
+    if (rw4) lbft_event_loop_kernel<NMAX, QS, 4><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);       \
+    else lbft_event_loop_kernel<NMAX, QS, 0><<<blocks, kBlockThreads, 0, s->stream>>>(s->P);           \
+  } while (0)
+  if (s->P.L.queue_scan) LBFT_LAUNCH(16, true);
+  else if (s->N <= 16) LBFT_LAUNCH(16, false);
+  else if (s->N <= 32) LBFT_LAUNCH(32, false);
+  else LBFT_LAUNCH(64, false);
+#undef LBFT_LAUNCH
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));

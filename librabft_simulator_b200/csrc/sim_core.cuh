@@ -22,6 +22,12 @@
 // per-round bitsets (block known, QC known, state pending) instead of hash maps.  Request/Response
 // events carry no payload because the reference answers a request on the requester itself
 // (simulator.rs:446), which makes the response a no-op for the record store.
+//
+// Shape of the hot loop (what the SIMT hardware wants): one event per iteration; the receiving node's
+// whole state (scalars, author masks and — for round_cap <= 128 — the three round bitsets) is pulled
+// into registers with ONE batch of independent coalesced loads, updated by branch-light code, and
+// written back once; every network send of the iteration goes through ONE copy of the delay-sampling +
+// enqueue code; the rare ziggurat wedge/tail and the exp() fallback live out of line.
 #pragma once
 #include <stdint.h>
 
@@ -29,8 +35,10 @@
 
 #if defined(__CUDACC__)
 #define LBFT_HD __host__ __device__ __forceinline__
+#define LBFT_COLD __host__ __device__ __noinline__
 #else
 #define LBFT_HD inline
+#define LBFT_COLD __attribute__((noinline))
 #include <cmath>
 #endif
 
@@ -132,18 +140,15 @@ struct SipWords {
 // (word w -> tile[w*STRIDE + lane]); the scan queue's 64-bit entries are interleaved at 8-byte granularity
 // (entry j of the region starting at word wbase -> tile[wbase*STRIDE + j*2*STRIDE + lane*2 .. +1]), so a warp
 // reading entry j issues one 256-byte coalesced access.
-template <int STRIDE>
+template <int STRIDE_>
 struct TileMem {
+  static constexpr int STRIDE = STRIDE_;
   uint32_t* tile;  // first word of the tile
   uint32_t lane;
+  LBFT_HD uint32_t* at(uint32_t w) const { return tile + (size_t)w * STRIDE + lane; }  // then p[k * STRIDE]
   LBFT_HD uint32_t ld(uint32_t w) const { return tile[(size_t)w * STRIDE + lane]; }
   LBFT_HD void st(uint32_t w, uint32_t v) const { tile[(size_t)w * STRIDE + lane] = v; }
-  LBFT_HD uint64_t ld64(uint32_t wbase, uint32_t j) const {
-    return *reinterpret_cast<const uint64_t*>(tile + (size_t)wbase * STRIDE + (size_t)j * 2 * STRIDE + lane * 2);
-  }
-  LBFT_HD void st64(uint32_t wbase, uint32_t j, uint64_t v) const {
-    *reinterpret_cast<uint64_t*>(tile + (size_t)wbase * STRIDE + (size_t)j * 2 * STRIDE + lane * 2) = v;
-  }
+  LBFT_HD uint64_t* at64(uint32_t wbase) const { return reinterpret_cast<uint64_t*>(tile + (size_t)wbase * STRIDE + lane * 2); }  // then q[j * STRIDE]
 };
 
 // List of authors used for the shuffled fan-out (simulator.rs:326-343, 356-370).
@@ -153,20 +158,34 @@ template <>
 struct AuthorList<16> {  // nibble-packed, lives in one 64-bit register
   uint64_t v = 0;
   uint32_t len = 0;
+  LBFT_HD void clear() { v = 0; len = 0; }
   LBFT_HD void push(uint32_t a) { v |= (uint64_t)a << (4 * len); len++; }
   LBFT_HD uint32_t get(uint32_t i) const { return (uint32_t)(v >> (4 * i)) & 15u; }
   LBFT_HD void swap(uint32_t i, uint32_t j) {
     uint64_t d = ((v >> (4 * i)) ^ (v >> (4 * j))) & 15u;
     v ^= (d << (4 * i)) | (d << (4 * j));
   }
+  LBFT_HD void fill_others(uint32_t n_nodes, uint32_t self) {  // 0..n-1 without `self`, ascending
+    const uint64_t iota = 0xfedcba9876543210ULL;
+    uint64_t lowmask = self ? ((1ULL << (4 * self)) - 1) : 0;
+    v = (iota & lowmask) | ((iota >> 4) & ~lowmask);
+    len = n_nodes - 1;
+    if (len < 16) v &= (1ULL << (4 * len)) - 1;
+  }
 };
 template <>
 struct AuthorList<64> {
   uint8_t a[64];
   uint32_t len = 0;
+  LBFT_HD void clear() { len = 0; }
   LBFT_HD void push(uint32_t x) { a[len++] = (uint8_t)x; }
   LBFT_HD uint32_t get(uint32_t i) const { return a[i]; }
   LBFT_HD void swap(uint32_t i, uint32_t j) { uint8_t t = a[i]; a[i] = a[j]; a[j] = t; }
+  LBFT_HD void fill_others(uint32_t n_nodes, uint32_t self) {
+    len = 0;
+    for (uint32_t i = 0; i < n_nodes; i++)
+      if (i != self) a[len++] = (uint8_t)i;
+  }
 };
 
 struct Actions {  // NodeUpdateActions, interfaces.rs:12-21 (should_send holds at most one author)
@@ -175,8 +194,61 @@ struct Actions {  // NodeUpdateActions, interfaces.rs:12-21 (should_send holds a
   bool broadcast, query_all;
 };
 
-template <class Mem, int NMAX, bool QSCAN>
+// ---- out-of-line cold paths (keep the hot loop's instruction footprint small) --------------------
+struct NormalSlow {
+  uint64_t s0, s1, s2, s3;
+  uint32_t draws;
+  int32_t accepted;
+  double x;
+};
+LBFT_HD uint64_t xoshiro_next(uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
+  uint64_t result = rotl64(s1 * 5, 7) * 9;
+  uint64_t t = s1 << 17;
+  s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3;
+  s2 ^= t;
+  s3 = rotl64(s3, 45);
+  return result;
+}
+// rand_distr 0.4.0 ziggurat, the parts after the fast accept: layer-0 tail (zero_case) and wedge test.
+LBFT_COLD NormalSlow normal_slow(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3, uint32_t draws, uint32_t i, double u, double x,
+                                 double f0, double f1, double zig_r) {
+  NormalSlow o;
+  o.accepted = 1;
+  o.x = x;
+  if (i == 0) {
+    double xx = 1.0, yy = 0.0;
+    while (mul_rn(-2.0, yy) < mul_rn(xx, xx)) {
+      double a = bits_to_f64((1023ULL << 52) | (xoshiro_next(s0, s1, s2, s3) >> 12)) - (1.0 - 2.220446049250313e-16 / 2.0);  // Open01
+      double b = bits_to_f64((1023ULL << 52) | (xoshiro_next(s0, s1, s2, s3) >> 12)) - (1.0 - 2.220446049250313e-16 / 2.0);
+      draws += 2;
+      xx = log(a) / zig_r;
+      yy = log(b);
+    }
+    o.x = u < 0.0 ? xx - zig_r : zig_r - xx;
+  } else {
+    double g = mul_rn((double)(xoshiro_next(s0, s1, s2, s3) >> 11), 1.0 / 9007199254740992.0);
+    draws += 1;
+    double lhs = add_rn(f1, mul_rn(f0 - f1, g));
+    double rhs = exp(mul_rn(-x, x) / 2.0);
+    o.accepted = lhs < rhs ? 1 : 0;
+  }
+  o.s0 = s0; o.s1 = s1; o.s2 = s2; o.s3 = s3;
+  o.draws = draws;
+  return o;
+}
+// LogNormal delay through the device exp(): only used when no threshold table could be built.
+LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 set: near-integer advisory
+  double v = exp(add_rn(mu, mul_rn(sigma, z)));
+  double r = rint(v);
+  int64_t flag = fabs(v - r) < 1e-9 * (r > 1.0 ? r : 1.0) ? (1LL << 62) : 0;
+  if (!(v < 1.0e9)) return (1LL << 61) | 1000000000LL;
+  return flag | (int64_t)v;
+}
+
+// RW = number of 32-bit words of each per-round bitset held in registers (0: bitsets stay in memory).
+template <class Mem, int NMAX, bool QSCAN, int RW>
 struct Core {
+  static constexpr int S = Mem::STRIDE;
   const Params& P;
   const Layout& L;
   Mem m;
@@ -211,12 +283,7 @@ struct Core {
   }
   LBFT_HD uint64_t next_u64() {
     draws++;
-    uint64_t result = rotl64(s1 * 5, 7) * 9;
-    uint64_t t = s1 << 17;
-    s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3;
-    s2 ^= t;
-    s3 = rotl64(s3, 45);
-    return result;
+    return xoshiro_next(s0, s1, s2, s3);
   }
   LBFT_HD uint32_t gen_range_u32(uint32_t n) {  // UniformInt<u32>::sample_single_inclusive(0, n-1)
     uint32_t zone = (n << clz32(n)) - 1;
@@ -234,7 +301,6 @@ struct Core {
       if (lo <= zone) return mulhi64(v, n);
     }
   }
-  LBFT_HD double open01() { return bits_to_f64((1023ULL << 52) | (next_u64() >> 12)) - (1.0 - 2.220446049250313e-16 / 2.0); }
   LBFT_HD double standard_normal() {  // rand_distr ziggurat, 256 layers
     for (;;) {
       uint64_t bits = next_u64();
@@ -242,22 +308,11 @@ struct Core {
       double u = bits_to_f64((1024ULL << 52) | (bits >> 12)) - 3.0;
       double xi = zx[i], xi1 = zx[i + 1];
       double x = mul_rn(u, xi);
-      if (fabs(x) < xi1) return x;
-      if (i == 0) {
-        double xx = 1.0, yy = 0.0;
-        while (mul_rn(-2.0, yy) < mul_rn(xx, xx)) {
-          double a = open01();
-          double b = open01();
-          xx = log(a) / P.zig_r;
-          yy = log(b);
-        }
-        return u < 0.0 ? xx - P.zig_r : P.zig_r - xx;
-      }
-      double g = mul_rn((double)(next_u64() >> 11), 1.0 / 9007199254740992.0);
-      double f0 = zf[i], f1 = zf[i + 1];
-      double lhs = add_rn(f1, mul_rn(f0 - f1, g));
-      double rhs = exp(mul_rn(-x, x) / 2.0);
-      if (lhs < rhs) return x;
+      if (fabs(x) < xi1) return x;  // ~98.8 % of the draws
+      NormalSlow o = normal_slow(s0, s1, s2, s3, draws, i, u, x, zf[i], zf[i + 1], P.zig_r);
+      s0 = o.s0; s1 = o.s1; s2 = o.s2; s3 = o.s3;
+      draws = o.draws;
+      if (o.accepted) return o.x;
     }
   }
   // GlobalTime::add_delay (simulator.rs:110-118): returns the delay in ms.
@@ -276,56 +331,110 @@ struct Core {
       while (z < thr[k]) k--;
       return k;
     }
-    double v = exp(add_rn(P.mu, mul_rn(P.sigma, z)));
-    double r = rint(v);
-    if (fabs(v - r) < 1e-9 * (r > 1.0 ? r : 1.0)) status |= ST_DELAY_NEAR_INT;
-    if (!(v < 1.0e9)) { status |= ST_TIME_OVERFLOW; return 1000000000; }
-    return (int32_t)(int64_t)v;
+    int64_t r = delay_via_exp(P.mu, P.sigma, z);
+    if (r & (1LL << 62)) status |= ST_DELAY_NEAR_INT;
+    if (r & (1LL << 61)) status |= ST_TIME_OVERFLOW;
+    return (int32_t)(r & 0x7fffffff);
   }
 
   // ------------------------------------------------------------------------------------------
   // memory helpers
   // ------------------------------------------------------------------------------------------
   LBFT_HD uint32_t nbase(uint32_t n) const { return L.node_base + n * L.node_words; }
-  LBFT_HD uint64_t ld_mask(uint32_t w) const {
-    uint64_t v = m.ld(w);
-    if (NMAX > 32) v |= (uint64_t)m.ld(w + 1) << 32;
+  LBFT_HD static uint64_t ld_mask(const uint32_t* p) {
+    uint64_t v = p[0];
+    if (NMAX > 32) v |= (uint64_t)p[S] << 32;
     return v;
   }
-  LBFT_HD void st_mask(uint32_t w, uint64_t v) const {
-    m.st(w, (uint32_t)v);
-    if (NMAX > 32) m.st(w + 1, (uint32_t)(v >> 32));
+  LBFT_HD static void st_mask(uint32_t* p, uint64_t v) {
+    p[0] = (uint32_t)v;
+    if (NMAX > 32) p[S] = (uint32_t)(v >> 32);
   }
-  LBFT_HD uint32_t ld_u16(uint32_t w, uint32_t i) const { return (m.ld(w + (i >> 1)) >> (16 * (i & 1))) & 0xffffu; }
-  LBFT_HD void st_u16(uint32_t w, uint32_t i, uint32_t v) const {
-    uint32_t x = m.ld(w + (i >> 1));
+  LBFT_HD static uint32_t ld_u16(const uint32_t* p, uint32_t i) { return (p[(i >> 1) * S] >> (16 * (i & 1))) & 0xffffu; }
+  LBFT_HD static void st_u16(uint32_t* p, uint32_t i, uint32_t v) {
+    uint32_t x = p[(i >> 1) * S];
     uint32_t sh = 16 * (i & 1);
-    m.st(w + (i >> 1), (x & ~(0xffffu << sh)) | (v << sh));
+    p[(i >> 1) * S] = (x & ~(0xffffu << sh)) | (v << sh);
   }
-  LBFT_HD bool bit_test(uint32_t w, uint32_t r) const { return (m.ld(w + (r >> 5)) >> (r & 31)) & 1u; }
-  LBFT_HD void bit_set(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) | (1u << (r & 31))); }
-  LBFT_HD void bit_clear(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) & ~(1u << (r & 31))); }
+  LBFT_HD bool mbit_test(uint32_t w, uint32_t r) const { return (m.ld(w + (r >> 5)) >> (r & 31)) & 1u; }
+  LBFT_HD void mbit_set(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) | (1u << (r & 31))); }
   LBFT_HD uint32_t chain_prev(uint32_t r) const { return m.ld(L.chain_base + 2 * r) & 0xffffu; }
 
+  // The receiving node's state, held in registers for the duration of one event.
   struct NodeRegs {
     uint32_t f[F_NSCALAR];
+    uint64_t vmask, tmask, tcmask;  // current_votes / current_timeouts / highest TC author sets
+    uint32_t hb[RW ? RW : 1], hq[RW ? RW : 1], pd[RW ? RW : 1];  // block known / QC known / state pending, by round
+    uint32_t* nb;  // this node's block in the tile
+    bool bits_dirty;
   };
   LBFT_HD void load_node(uint32_t n, NodeRegs& d) const {
-    uint32_t b = nbase(n);
+    uint32_t* nb = m.at(nbase(n));
+    d.nb = nb;
 #pragma unroll
-    for (int i = 0; i < (int)F_NSCALAR; i++) d.f[i] = m.ld(b + i);
-  }
-  LBFT_HD void store_node(uint32_t n, const NodeRegs& d) const {
-    uint32_t b = nbase(n);
+    for (int i = 0; i < (int)F_NSCALAR; i++) d.f[i] = nb[i * S];
+    d.vmask = ld_mask(nb + L.n_vmask * S);
+    d.tmask = ld_mask(nb + L.n_tmask * S);
+    d.tcmask = ld_mask(nb + L.n_tcmask * S);
+    if (RW) {
 #pragma unroll
-    for (int i = 0; i < (int)F_NSCALAR; i++) m.st(b + i, d.f[i]);
+      for (int i = 0; i < (RW ? RW : 1); i++) {
+        d.hb[i] = nb[(L.n_hasblk + i) * S];
+        d.hq[i] = nb[(L.n_hasqc + i) * S];
+        d.pd[i] = nb[(L.n_pend + i) * S];
+      }
+    }
+    d.bits_dirty = false;
   }
+  LBFT_HD void store_node(const NodeRegs& d) const {
+    uint32_t* nb = d.nb;
+#pragma unroll
+    for (int i = 0; i < (int)F_NSCALAR; i++) nb[i * S] = d.f[i];
+    st_mask(nb + L.n_vmask * S, d.vmask);
+    st_mask(nb + L.n_tmask * S, d.tmask);
+    st_mask(nb + L.n_tcmask * S, d.tcmask);
+    if (RW && d.bits_dirty) {
+#pragma unroll
+      for (int i = 0; i < (RW ? RW : 1); i++) {
+        nb[(L.n_hasblk + i) * S] = d.hb[i];
+        nb[(L.n_hasqc + i) * S] = d.hq[i];
+        nb[(L.n_pend + i) * S] = d.pd[i];
+      }
+    }
+  }
+  // round-bitset accessors: registers when RW > 0, memory otherwise
+  LBFT_HD static bool rget(const uint32_t (&a)[RW ? RW : 1], uint32_t r) {
+    uint32_t w = a[0];
+#pragma unroll
+    for (int i = 1; i < (RW ? RW : 1); i++) w = ((r >> 5) == (uint32_t)i) ? a[i] : w;
+    return (w >> (r & 31)) & 1u;
+  }
+  LBFT_HD static void rput(uint32_t (&a)[RW ? RW : 1], uint32_t r, bool on) {
+    uint32_t bit = 1u << (r & 31);
+#pragma unroll
+    for (int i = 0; i < (RW ? RW : 1); i++)
+      if ((r >> 5) == (uint32_t)i) a[i] = on ? (a[i] | bit) : (a[i] & ~bit);
+  }
+  LBFT_HD bool has_blk(const NodeRegs& d, uint32_t r) const { return RW ? rget(d.hb, r) : ((d.nb[(L.n_hasblk + (r >> 5)) * S] >> (r & 31)) & 1u); }
+  LBFT_HD bool has_qc(const NodeRegs& d, uint32_t r) const { return RW ? rget(d.hq, r) : ((d.nb[(L.n_hasqc + (r >> 5)) * S] >> (r & 31)) & 1u); }
+  LBFT_HD bool is_pend(const NodeRegs& d, uint32_t r) const { return RW ? rget(d.pd, r) : ((d.nb[(L.n_pend + (r >> 5)) * S] >> (r & 31)) & 1u); }
+  LBFT_HD void mem_put(NodeRegs& d, uint32_t base, uint32_t r, bool on) const {
+    uint32_t* p = d.nb + (base + (r >> 5)) * S;
+    uint32_t bit = 1u << (r & 31);
+    *p = on ? (*p | bit) : (*p & ~bit);
+  }
+  LBFT_HD void set_blk(NodeRegs& d, uint32_t r) const { if (RW) { rput(d.hb, r, true); d.bits_dirty = true; } else mem_put(d, L.n_hasblk, r, true); }
+  LBFT_HD void set_qc(NodeRegs& d, uint32_t r) const { if (RW) { rput(d.hq, r, true); d.bits_dirty = true; } else mem_put(d, L.n_hasqc, r, true); }
+  LBFT_HD void set_pend(NodeRegs& d, uint32_t r, bool on) const { if (RW) { rput(d.pd, r, on); d.bits_dirty = true; } else mem_put(d, L.n_pend, r, on); }
+
   LBFT_HD static uint32_t election(const NodeRegs& d) { return (d.f[F_FLAGS] & FL_ELECTION_MASK) >> FL_ELECTION_SHIFT; }
   LBFT_HD static void set_election(NodeRegs& d, uint32_t e) { d.f[F_FLAGS] = (d.f[F_FLAGS] & ~FL_ELECTION_MASK) | (e << FL_ELECTION_SHIFT); }
   LBFT_HD static uint32_t leader_of(const NodeRegs& d) { return (d.f[F_FLAGS] >> FL_LEADER_SHIFT) & 0xffu; }
 
   // ------------------------------------------------------------------------------------------
-  // pending-event queue: binary min-heap on (time, 3-kind, stamp)  (simulator.rs:149-161)
+  // pending-event queue, ordered by (time, 3-kind, stamp)  (simulator.rs:149-161)
+  //   QSCAN: unsorted array of 64-bit keys, O(1) append, linear min-scan on pop
+  //   else : binary min-heap with 3-word entries
   // ------------------------------------------------------------------------------------------
   LBFT_HD uint64_t heap_key_at(uint32_t i) const { return ((uint64_t)m.ld(L.heap_time + i) << 32) | m.ld(L.heap_key + i); }
   LBFT_HD void heap_move(uint32_t dst, uint32_t src) const {
@@ -342,11 +451,11 @@ struct Core {
     if (time > P.max_clock) return false;
     if (qsize >= L.queue_cap) { status |= ST_QUEUE_OVERFLOW; return false; }
     if (QSCAN) {
-      // unsorted array, O(1) append.  key = time:24 | 3-kind:2 | stamp:22 | slot:8 | sender:4 | receiver:4;
-      // stamps are unique, so the payload bits below them never decide a comparison.
+      // key = time:24 | 3-kind:2 | stamp:22 | slot:8 | sender:4 | receiver:4; stamps are unique, so the
+      // payload bits below them never decide a comparison.
       uint64_t key = ((uint64_t)(uint32_t)time << 40) | ((uint64_t)(3u - kind) << 38) | ((uint64_t)st << 16) |
                      (uint64_t)(((data >> 16) & 0xffu) << 8) | (uint64_t)(((data >> 8) & 0xfu) << 4) | (uint64_t)(data & 0xfu);
-      m.st64(L.heap_time, qsize, key);
+      m.at64(L.heap_time)[(size_t)qsize * S] = key;
       qsize++;
       if (qsize > max_queue) max_queue = qsize;
       return true;
@@ -369,24 +478,27 @@ struct Core {
   LBFT_HD void pop_event(int32_t& time, uint32_t& kind, uint32_t& data) {
     if (QSCAN) {
       // linear min-scan: independent, fully coalesced loads; no data-dependent sift chains
-      uint64_t best = m.ld64(L.heap_time, 0);
+      const uint64_t* q = m.at64(L.heap_time);
+      uint64_t best = q[0];
       uint32_t bi = 0;
       const uint32_t n = qsize;
       uint32_t j = 1;
+#pragma unroll 1
       for (; j + 3 < n; j += 4) {
-        uint64_t k0 = m.ld64(L.heap_time, j), k1 = m.ld64(L.heap_time, j + 1), k2 = m.ld64(L.heap_time, j + 2),
-                 k3 = m.ld64(L.heap_time, j + 3);
+        uint64_t k0 = q[(size_t)j * S], k1 = q[(size_t)(j + 1) * S], k2 = q[(size_t)(j + 2) * S], k3 = q[(size_t)(j + 3) * S];
         if (k0 < best) { best = k0; bi = j; }
         if (k1 < best) { best = k1; bi = j + 1; }
         if (k2 < best) { best = k2; bi = j + 2; }
         if (k3 < best) { best = k3; bi = j + 3; }
       }
+#pragma unroll 1
       for (; j < n; j++) {
-        uint64_t k0 = m.ld64(L.heap_time, j);
+        uint64_t k0 = q[(size_t)j * S];
         if (k0 < best) { best = k0; bi = j; }
       }
       qsize = n - 1;
-      if (bi != n - 1) m.st64(L.heap_time, bi, m.ld64(L.heap_time, n - 1));
+      uint64_t* qw = m.at64(L.heap_time);
+      if (bi != n - 1) qw[(size_t)bi * S] = qw[(size_t)(n - 1) * S];
       time = (int32_t)(best >> 40);
       kind = 3u - ((uint32_t)(best >> 38) & 3u);
       uint32_t lo = (uint32_t)best & 0xffffu, slot = lo >> 8;
@@ -437,124 +549,110 @@ struct Core {
     m.st(L.pay_base + s * L.pay_words + 2, pay_free);
     pay_free = s;
   }
+  LBFT_HD void pay_unref(uint32_t slot, uint32_t w2) {
+    uint32_t refs = (w2 & 0xffffu) - 1;
+    if (refs == 0) pay_release(slot);
+    else m.st(L.pay_base + slot * L.pay_words + 2, (w2 & 0xffff0000u) | refs);
+  }
 
   // ------------------------------------------------------------------------------------------
   // record store in round-id form
   // ------------------------------------------------------------------------------------------
   // update_current_round, record_store.rs:207-219
-  LBFT_HD void update_current_round(uint32_t n, NodeRegs& d, uint32_t round) {
+  LBFT_HD void update_current_round(NodeRegs& d, uint32_t round) {
     if (round <= d.f[F_CUR]) return;
     if (round >= L.round_cap) { status |= ST_ROUND_OVERFLOW; return; }
     d.f[F_CUR] = round;
     d.f[F_FLAGS] &= ~(FL_PROPOSED | FL_ELECTION_MASK);
-    st_mask(nbase(n) + L.n_tmask, 0);
-    st_mask(nbase(n) + L.n_vmask, 0);
+    d.tmask = 0;
+    d.vmask = 0;
     d.f[F_TOW] = 0;
     d.f[F_BALLOT] = 0;
   }
   // Is the execution state of the block certified by QC `prev` (0 = the epoch's initial state)
   // available to SimulatedContext::compute?  simulated_context.rs:102-108, 128-157
-  LBFT_HD bool state_available(uint32_t n, const NodeRegs& d, uint32_t prev) const {
+  LBFT_HD bool state_available(const NodeRegs& d, uint32_t prev) const {
     if (d.f[F_LC_ROUND] == prev) return true;
     if (prev == 0) return false;
-    return bit_test(nbase(n) + L.n_pend, prev);
+    return is_pend(d, prev);
   }
   // Record::Block — verify :263-291, insert :466-476
-  LBFT_HD void insert_block(uint32_t n, NodeRegs& d, uint32_t r) {
-    uint32_t b = nbase(n);
-    if (bit_test(b + L.n_hasblk, r)) return;  // "Block was already inserted."
+  LBFT_HD void insert_block(NodeRegs& d, uint32_t r) {
+    if (has_blk(d, r)) return;  // "Block was already inserted."
     uint32_t prev = chain_prev(r);
-    if (prev != 0 && !bit_test(b + L.n_hasqc, prev)) return;  // "The previous QC (if any) must be verified first."
+    if (prev != 0 && !has_qc(d, prev)) return;  // "The previous QC (if any) must be verified first."
     // rounds are increasing by construction (the proposer's hqc round is below its current round)
     if (r == d.f[F_CUR]) d.f[F_FLAGS] |= FL_PROPOSED;  // author == leader(round) by construction (C.1)
-    bit_set(b + L.n_hasblk, r);
+    set_blk(d, r);
   }
   // Record::Vote — verify :292-329, insert :477-499
-  LBFT_HD void insert_vote(uint32_t n, NodeRegs& d, uint32_t r, uint32_t author) {
-    uint32_t b = nbase(n);
+  LBFT_HD void insert_vote(NodeRegs& d, uint32_t r, uint32_t author) {
     if (r != d.f[F_CUR]) return;
-    if (!bit_test(b + L.n_hasblk, r)) return;
-    uint64_t vm = ld_mask(b + L.n_vmask);
-    if ((vm >> author) & 1) return;
-    st_mask(b + L.n_vmask, vm | (1ULL << author));
+    if (!has_blk(d, r)) return;
+    if ((d.vmask >> author) & 1) return;
+    d.vmask |= 1ULL << author;
     if (election(d) == 0) {
       d.f[F_BALLOT] += P.weights[author];
       if (d.f[F_BALLOT] >= P.quorum) set_election(d, 1);
     }
   }
   // Record::QuorumCertificate — verify :330-389, insert :500-526
-  LBFT_HD void insert_qc(uint32_t n, NodeRegs& d, uint32_t r) {
-    uint32_t b = nbase(n);
-    if (bit_test(b + L.n_hasqc, r)) return;    // "QuorumCertificate was already inserted."
-    if (!bit_test(b + L.n_hasblk, r)) return;  // "The certified block hash of a QC must be verified first."
-    bit_set(b + L.n_hasqc, r);                 // inserted before execution (:505)
+  LBFT_HD void insert_qc(NodeRegs& d, uint32_t r) {
+    if (has_qc(d, r)) return;    // "QuorumCertificate was already inserted."
+    if (!has_blk(d, r)) return;  // "The certified block hash of a QC must be verified first."
+    set_qc(d, r);                // inserted before execution (:505)
     uint32_t prev = chain_prev(r);
-    if (!state_available(n, d, prev)) return;  // "I failed to execute a block with a QC" — QC stays in the map
-    bit_set(b + L.n_pend, r);
+    if (!state_available(d, prev)) return;  // "I failed to execute a block with a QC" — QC stays in the map
+    set_pend(d, r, true);
     if (r > d.f[F_HQC]) d.f[F_HQC] = r;
-    update_current_round(n, d, r + 1);
+    update_current_round(d, r + 1);
     // update_commit_3chain_round :221-235
-    if (prev != 0) {
+    if (prev != 0 && r == prev + 1 && prev - 1 > d.f[F_HCR]) {
       uint32_t r1 = chain_prev(prev);
-      if (r1 != 0 && r == prev + 1 && prev == r1 + 1 && r1 > d.f[F_HCR]) {
+      if (r1 != 0 && prev == r1 + 1) {
         d.f[F_HCR] = r1;
         d.f[F_HCC] = r;
       }
     }
   }
   // Record::Timeout — verify :390-415, insert :527-538
-  LBFT_HD void insert_timeout(uint32_t n, NodeRegs& d, uint32_t round, uint32_t hcbr, uint32_t author) {
-    uint32_t b = nbase(n);
+  LBFT_HD void insert_timeout(NodeRegs& d, uint32_t round, uint32_t hcbr, uint32_t author) {
     if (hcbr > d.f[F_HQC]) return;
     if (round != d.f[F_CUR]) return;
-    uint64_t tm = ld_mask(b + L.n_tmask);
-    if ((tm >> author) & 1) return;
-    tm |= 1ULL << author;
-    st_mask(b + L.n_tmask, tm);
-    st_u16(b + L.n_thcbr, author, hcbr);
+    if ((d.tmask >> author) & 1) return;
+    d.tmask |= 1ULL << author;
+    st_u16(d.nb + L.n_thcbr * S, author, hcbr);
     d.f[F_TOW] += P.weights[author];
     if (d.f[F_TOW] >= P.quorum) {
-      st_mask(b + L.n_tcmask, tm);
-      for (uint32_t i = 0; i < L.hcbr_words; i++) m.st(b + L.n_tchcbr + i, m.ld(b + L.n_thcbr + i));
+      d.tcmask = d.tmask;
+      for (uint32_t i = 0; i < L.hcbr_words; i++) d.nb[(L.n_tchcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
       d.f[F_TC_ROUND] = d.f[F_CUR];
       d.f[F_FLAGS] |= FL_HAS_TC;
       d.f[F_HTC] = d.f[F_CUR];
-      update_current_round(n, d, d.f[F_CUR] + 1);
+      update_current_round(d, d.f[F_CUR] + 1);
     }
   }
   // propose_block :655-674 (+ CommandFetcher::fetch, simulated_context.rs:116-125)
-  LBFT_HD void propose_block(uint32_t n, NodeRegs& d, uint32_t prev_round, int32_t clk) {
+  LBFT_HD void propose_block(NodeRegs& d, uint32_t prev_round, int32_t clk) {
     uint32_t idx = d.f[F_NEXT_CMD]++;
     uint32_t r = d.f[F_CUR];
     if (idx > 0xffffu) status |= ST_ROUND_OVERFLOW;
-    if (bit_test(L.created_base, r)) status |= ST_INVARIANT;  // App. C.1: second block in a round
-    bit_set(L.created_base, r);
+    if (mbit_test(L.created_base, r)) status |= ST_INVARIANT;  // App. C.1: second block in a round
+    mbit_set(L.created_base, r);
     m.st(L.chain_base + 2 * r, prev_round | (idx << 16));
     m.st(L.chain_base + 2 * r + 1, (uint32_t)clk);
-    insert_block(n, d, r);
+    insert_block(d, r);
   }
   // create_vote :676-700
-  LBFT_HD bool create_vote(uint32_t n, NodeRegs& d, uint32_t r) {
-    uint32_t prev = chain_prev(r);
-    if (!state_available(n, d, prev)) return false;
-    bit_set(nbase(n) + L.n_pend, r);
-    insert_vote(n, d, r, n);
-    return true;
-  }
-  // check_for_new_quorum_certificate :702-738
-  LBFT_HD bool check_for_new_qc(uint32_t n, NodeRegs& d) {
-    if (election(d) != 1) return false;
-    uint32_t r = d.f[F_CUR];
-    if (P.leader[r] != n) return false;
-    set_election(d, 2);
-    if (bit_test(L.qcmade_base, r)) status |= ST_INVARIANT;  // App. C.1: second QC in a round
-    bit_set(L.qcmade_base, r);
-    insert_qc(n, d, r);
+  LBFT_HD bool create_vote(NodeRegs& d, uint32_t n, uint32_t r, uint32_t prev) {
+    if (!state_available(d, prev)) return false;
+    set_pend(d, r, true);
+    insert_vote(d, r, n);
     return true;
   }
   // process_commits node.rs:313-350 over committed_states_after record_store.rs:557-574 and
   // StateFinalizer::commit simulated_context.rs:161-185
-  LBFT_HD void process_commits(uint32_t n, NodeRegs& d) {
+  LBFT_HD void process_commits(NodeRegs& d) {
     uint32_t after = d.f[F_TRK_HCR];
     uint32_t top = d.f[F_HCC] ? d.f[F_HCR] : 0;
     while (top > after) {
@@ -564,9 +662,8 @@ struct Core {
         if (p <= after) break;
         q = p;
       }
-      uint32_t b = nbase(n);
-      if (!bit_test(b + L.n_pend, q)) status |= ST_INVARIANT;   // "Committed states should be known"
-      bit_clear(b + L.n_pend, q);
+      if (!is_pend(d, q)) status |= ST_INVARIANT;  // "Committed states should be known"
+      set_pend(d, q, false);
       if (chain_prev(q) != d.f[F_LC_ROUND]) status |= ST_INVARIANT;  // happened_just_before
       d.f[F_LC_ROUND] = q;
       d.f[F_COMMITS]++;
@@ -584,7 +681,6 @@ struct Core {
     a.send_to = -1;
     a.broadcast = false;
     a.query_all = false;
-    const uint32_t b = nbase(n);
     // ---- Pacemaker::update_pacemaker, pacemaker.rs:142-207
     uint32_t active = (d.f[F_HQC] > d.f[F_HTC] ? d.f[F_HQC] : d.f[F_HTC]) + 1;
     if (active > d.f[F_PMR]) {
@@ -606,7 +702,7 @@ struct Core {
       a.broadcast = true;
       a.next = clk;
     }
-    bool has_timeout = active == d.f[F_CUR] && ((ld_mask(b + L.n_tmask) >> n) & 1);
+    bool has_timeout = active == d.f[F_CUR] && ((d.tmask >> n) & 1);
     if (!has_timeout) {
       int32_t deadline = (int32_t)d.f[F_PM_START] + (int32_t)d.f[F_PM_DUR];
       if (clk >= deadline) {
@@ -625,27 +721,36 @@ struct Core {
     // ---- process_pacemaker_actions, node.rs:179-202
     if (mk_timeout && propose) status |= ST_INVARIANT;  // App. C.1b
     if (mk_timeout) {
-      insert_timeout(n, d, active, d.f[F_HQC], n);  // create_timeout, record_store.rs:636-649
+      insert_timeout(d, active, d.f[F_HQC], n);  // create_timeout, record_store.rs:636-649
       if (active > d.f[F_LVR]) d.f[F_LVR] = active;
     }
-    if (propose) propose_block(n, d, d.f[F_HQC], clk);
+    if (propose) propose_block(d, d.f[F_HQC], clk);
     // ---- vote on the proposal, node.rs:255-276
     if (d.f[F_CUR] == d.f[F_PMR] && (d.f[F_FLAGS] & FL_PROPOSED)) {
       uint32_t r = d.f[F_CUR];
-      uint32_t prev = chain_prev(r);  // previous_round(), record_store.rs:588-598
-      if (r > d.f[F_LVR] && prev >= d.f[F_LOCKED]) {
-        d.f[F_LVR] = r;
-        uint32_t sp = prev ? chain_prev(prev) : 0;  // second_previous_round(), :600-609
-        if (sp > d.f[F_LOCKED]) d.f[F_LOCKED] = sp;
-        if (create_vote(n, d, r)) a.send_to = (int32_t)leader;
+      if (r > d.f[F_LVR]) {
+        uint32_t prev = chain_prev(r);  // previous_round(), record_store.rs:588-598
+        if (prev >= d.f[F_LOCKED]) {
+          d.f[F_LVR] = r;
+          uint32_t sp = prev ? chain_prev(prev) : 0;  // second_previous_round(), :600-609
+          if (sp > d.f[F_LOCKED]) d.f[F_LOCKED] = sp;
+          if (create_vote(d, n, r, prev)) a.send_to = (int32_t)leader;
+        }
       }
     }
-    // ---- QC creation, node.rs:277-283
-    if (check_for_new_qc(n, d)) {
-      a.broadcast = true;
-      a.next = clk;
+    // ---- check_for_new_quorum_certificate (record_store.rs:702-738) and QC broadcast, node.rs:277-283
+    if (election(d) == 1) {
+      uint32_t r = d.f[F_CUR];
+      if (P.leader[r] == n) {
+        set_election(d, 2);
+        if (mbit_test(L.qcmade_base, r)) status |= ST_INVARIANT;  // App. C.1: second QC in a round
+        mbit_set(L.qcmade_base, r);
+        insert_qc(d, r);
+        a.broadcast = true;
+        a.next = clk;
+      }
     }
-    process_commits(n, d);
+    process_commits(d);
     // ---- CommitTracker::update_tracker, node.rs:364-396
     if (d.f[F_HCR] > d.f[F_TRK_HCR]) {
       d.f[F_TRK_HCR] = d.f[F_HCR];
@@ -666,66 +771,61 @@ struct Core {
   // DataSyncNode::create_notification (data_sync.rs:82-111) into a payload slot
   // ------------------------------------------------------------------------------------------
   LBFT_HD void write_notification(uint32_t n, const NodeRegs& d, uint32_t slot, uint32_t refs) {
-    uint32_t pb = L.pay_base + slot * L.pay_words, b = nbase(n);
-    uint64_t tm = ld_mask(b + L.n_tmask);
+    uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
     bool has_tc = d.f[F_FLAGS] & FL_HAS_TC;
-    uint32_t vote = (uint32_t)((ld_mask(b + L.n_vmask) >> n) & 1);  // current_vote(author), record_store.rs:762-764
+    uint32_t vote = (uint32_t)((d.vmask >> n) & 1);  // current_vote(author), record_store.rs:762-764
     uint32_t prop = (d.f[F_CUR] == d.f[F_PMR] && (d.f[F_FLAGS] & FL_PROPOSED) && leader_of(d) == n) ? 1u : 0u;
-    m.st(pb + 0, d.f[F_HCC] | (d.f[F_HQC] << 16));
-    m.st(pb + 1, d.f[F_CUR] | ((has_tc ? d.f[F_TC_ROUND] : 0u) << 16));
-    m.st(pb + 2, refs | ((vote | (prop << 1)) << 16));
-    st_mask(pb + L.p_tcmask, has_tc ? ld_mask(b + L.n_tcmask) : 0);
-    st_mask(pb + L.p_curmask, tm);
+    pb[0] = d.f[F_HCC] | (d.f[F_HQC] << 16);
+    pb[1 * S] = d.f[F_CUR] | ((has_tc ? d.f[F_TC_ROUND] : 0u) << 16);
+    pb[2 * S] = refs | ((vote | (prop << 1)) << 16);
+    st_mask(pb + L.p_tcmask * S, has_tc ? d.tcmask : 0);
+    st_mask(pb + L.p_curmask * S, d.tmask);
     for (uint32_t i = 0; i < L.hcbr_words; i++) {
-      m.st(pb + L.p_tchcbr + i, m.ld(b + L.n_tchcbr + i));
-      m.st(pb + L.p_curhcbr + i, m.ld(b + L.n_thcbr + i));
+      pb[(L.p_tchcbr + i) * S] = d.nb[(L.n_tchcbr + i) * S];
+      pb[(L.p_curhcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
     }
   }
   // DataSyncNode::handle_notification (data_sync.rs:113-177).  Returns should_sync.
-  LBFT_HD bool handle_notification(uint32_t n, NodeRegs& d, uint32_t slot, uint32_t sender) {
-    uint32_t pb = L.pay_base + slot * L.pay_words;
-    uint32_t w0 = m.ld(pb), w1 = m.ld(pb + 1), w2 = m.ld(pb + 2);
+  LBFT_HD bool handle_notification(NodeRegs& d, uint32_t slot, uint32_t sender) {
+    uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
+    uint32_t w0 = pb[0], w1 = pb[1 * S], w2 = pb[2 * S];
+    uint64_t tcm = ld_mask(pb + L.p_tcmask * S), curm = ld_mask(pb + L.p_curmask * S);
     uint32_t hcc = w0 & 0xffffu, hqc = w0 >> 16, cur_s = w1 & 0xffffu, tc_round = w1 >> 16;
     bool vote = (w2 >> 16) & 1, prop = (w2 >> 17) & 1;
     bool should_sync = false;
-    if (hcc) {
-      insert_qc(n, d, hcc);
-      should_sync |= hcc > d.f[F_HCR] + 2;
+    // the two certificates, in message order: highest commit certificate, highest QC (one code copy)
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+      uint32_t q = which ? hqc : hcc;
+      if (q) {
+        insert_qc(d, q);
+        should_sync |= which ? (q > d.f[F_HQC]) : (q > d.f[F_HCR] + 2);
+      }
     }
-    if (hqc) {
-      insert_qc(n, d, hqc);
-      should_sync |= hqc > d.f[F_HQC];
-    }
-    if (prop) insert_block(n, d, cur_s);
+    if (prop) insert_block(d, cur_s);
     // timeouts: the TC's first, then the sender's current ones, ascending author.
     // A group whose round is not the receiver's current round is rejected wholesale, and accepting
     // a timeout can only move the receiver's round away from the group's round.
-    if (tc_round && tc_round == d.f[F_CUR]) {
-      uint64_t mask = ld_mask(pb + L.p_tcmask);
-      while (mask) {
-        uint32_t a = ctz64(mask);
-        mask &= mask - 1;
-        insert_timeout(n, d, tc_round, ld_u16(pb + L.p_tchcbr, a), a);
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+      uint32_t round = which ? cur_s : tc_round;
+      uint64_t mask = which ? curm : tcm;
+      if (round != 0 && round == d.f[F_CUR]) {
+        const uint32_t* hp = pb + (which ? L.p_curhcbr : L.p_tchcbr) * S;
+        while (mask) {
+          uint32_t a = ctz64(mask);
+          mask &= mask - 1;
+          insert_timeout(d, round, ld_u16(hp, a), a);
+        }
       }
     }
-    if (cur_s == d.f[F_CUR]) {
-      uint64_t mask = ld_mask(pb + L.p_curmask);
-      while (mask) {
-        uint32_t a = ctz64(mask);
-        mask &= mask - 1;
-        insert_timeout(n, d, cur_s, ld_u16(pb + L.p_curhcbr, a), a);
-      }
-    }
-    if (vote) insert_vote(n, d, cur_s, sender);
-    // release our reference on the payload
-    uint32_t refs = (w2 & 0xffffu) - 1;
-    if (refs == 0) pay_release(slot);
-    else m.st(pb + 2, (w2 & 0xffff0000u) | refs);
+    if (vote) insert_vote(d, cur_s, sender);
+    pay_unref(slot, w2);
     return should_sync;
   }
 
   // ------------------------------------------------------------------------------------------
-  // Simulator::process_node_actions, simulator.rs:296-378
+  // network sends: schedule_network_event (simulator.rs:266-269) + partition drop (extension)
   // ------------------------------------------------------------------------------------------
   LBFT_HD bool partitioned(uint32_t a, uint32_t b2) const {  // EXTENSION
     for (uint32_t k = 0; k < L.part_windows; k++) {
@@ -735,7 +835,6 @@ struct Core {
     }
     return false;
   }
-  // schedule_network_event :266-269 (+ partition drop).  Returns true if the event was queued.
   LBFT_HD bool schedule_network_event(uint32_t kind, uint32_t receiver, uint32_t sender, uint32_t slot) {
     int32_t t = clock + sample_delay();
     if (L.part_windows && partitioned(receiver, sender)) {
@@ -756,43 +855,6 @@ struct Core {
     }
     d.f[F_LAST_TIMER] = (uint32_t)t;
     push_event(t, EV_TIMER, n | (n << 8) | (PAY_NONE << 16));
-  }
-  LBFT_HD void process_node_actions(uint32_t n, NodeRegs& d, const Actions& a) {
-    const uint32_t N = L.num_nodes;
-    // next UpdateTimerEvent :311-324
-    int64_t from_node = a.next == NODE_TIME_NEVER ? (int64_t)0x7fffffff : (int64_t)a.next + (int32_t)d.f[F_STARTUP];
-    int64_t nt = from_node > (int64_t)clock + 1 ? from_node : (int64_t)clock + 1;
-    if (nt > 0x7ffffff0) nt = 0x7ffffff0;
-    d.f[F_IGNORE] = (uint32_t)((int32_t)nt - 1);
-    push_timer(n, d, (int32_t)nt);
-    // notifications :326-354
-    AuthorList<(NMAX <= 16 ? 16 : 64)> recv;
-    if (a.broadcast) {
-      for (uint32_t i = 0; i < N; i++)
-        if (i != n) recv.push(i);
-    } else if (a.send_to >= 0 && (uint32_t)a.send_to != n) {
-      recv.push((uint32_t)a.send_to);
-    }
-    for (uint32_t i = recv.len; i-- > 1;) recv.swap(i, gen_range_u32(i + 1));  // SliceRandom::shuffle
-    if (recv.len) {
-      uint32_t slot = pay_alloc();
-      uint32_t queued = 0;
-      sched_notify += recv.len;
-      for (uint32_t i = 0; i < recv.len; i++)
-        if (schedule_network_event(EV_NOTIFY, recv.get(i), n, slot)) queued++;
-      if (slot != PAY_NONE) {
-        if (queued) write_notification(n, d, slot, queued);
-        else pay_release(slot);
-      }
-    }
-    // requests :356-377
-    if (a.query_all) {
-      AuthorList<(NMAX <= 16 ? 16 : 64)> snd;
-      for (uint32_t i = 0; i < N; i++)
-        if (i != n) snd.push(i);
-      for (uint32_t i = snd.len; i-- > 1;) snd.swap(i, gen_range_u32(i + 1));
-      for (uint32_t i = 0; i < snd.len; i++) schedule_network_event(EV_REQUEST, n, snd.get(i), PAY_NONE);
-    }
   }
 
   // ------------------------------------------------------------------------------------------
@@ -824,6 +886,7 @@ struct Core {
       s0 = k0; s1 = k1; s2 = k2; s3 = k3;
       draws = kd;
     }
+#pragma unroll 1
     for (uint32_t n = 0; n < N; n++) {
       int32_t startup = sample_delay() + 1;
       uint32_t b = nbase(n);
@@ -837,51 +900,97 @@ struct Core {
   }
 
   // ------------------------------------------------------------------------------------------
-  // Simulator::loop_until, simulator.rs:380-475
+  // Simulator::loop_until, simulator.rs:380-475, with process_node_actions (:296-378) folded in
   // ------------------------------------------------------------------------------------------
   LBFT_HD void run() {
+    const uint32_t N = L.num_nodes;
+#pragma unroll 1
     while (qsize > 0 && !(status & ST_FATAL)) {
       int32_t t;
       uint32_t kind, data;
       pop_event(t, kind, data);
       if (t > P.max_clock) break;  // unreachable: such events are dropped at push
       if (t > clock) clock = t;
-      uint32_t receiver = data & 0xffu, sender = (data >> 8) & 0xffu, slot = data >> 16;
-      if (kind == EV_NOTIFY) proc0++;
-      else if (kind == EV_REQUEST) proc1++;
-      else if (kind == EV_RESPONSE) proc2++;
-      else proc3++;
+      const uint32_t receiver = data & 0xffu, sender = (data >> 8) & 0xffu, slot = data >> 16;
+      proc0 += kind == EV_NOTIFY;
+      proc1 += kind == EV_REQUEST;
+      proc2 += kind == EV_RESPONSE;
+      proc3 += kind == EV_TIMER;
       // EXTENSION D.2: silent nodes handle nothing and answer no request
       if (P.silent_mask) {
         bool drop = (P.silent_mask >> receiver) & 1;
         if (kind == EV_REQUEST && ((P.silent_mask >> sender) & 1)) drop = true;
         if (drop) {
-          if (kind == EV_NOTIFY) {  // still release the payload reference
-            uint32_t pb = L.pay_base + slot * L.pay_words;
-            uint32_t w2 = m.ld(pb + 2), refs = (w2 & 0xffffu) - 1;
-            if (refs == 0) pay_release(slot);
-            else m.st(pb + 2, (w2 & 0xffff0000u) | refs);
-          }
+          if (kind == EV_NOTIFY) pay_unref(slot, m.ld(L.pay_base + slot * L.pay_words + 2));
           continue;
         }
       }
-      if (kind == EV_REQUEST) {
-        // answered by `receiver` itself (simulator.rs:446): no state change, one delay draw
-        schedule_network_event(EV_RESPONSE, receiver, sender, PAY_NONE);
-        continue;
-      }
       NodeRegs d;
-      load_node(receiver, d);
-      if (kind == EV_TIMER && clock <= (int32_t)d.f[F_IGNORE]) {
-        cancelled++;
-        continue;
-      }
+      Actions a;
+      a.next = NODE_TIME_NEVER;
+      a.send_to = -1;
+      a.broadcast = false;
+      a.query_all = false;
       bool should_sync = false;
-      if (kind == EV_NOTIFY) should_sync = handle_notification(receiver, d, slot, sender);
-      Actions a = update_node(receiver, d, clock - (int32_t)d.f[F_STARTUP]);
-      if (should_sync) schedule_network_event(EV_REQUEST, receiver, sender, PAY_NONE);  // :427-433
-      process_node_actions(receiver, d, a);
-      store_node(receiver, d);
+      const bool is_request = kind == EV_REQUEST;  // answered by `receiver` itself (simulator.rs:446): no state change
+      if (!is_request) {
+        load_node(receiver, d);
+        if (kind == EV_TIMER && clock <= (int32_t)d.f[F_IGNORE]) {
+          cancelled++;
+          continue;
+        }
+        if (kind == EV_NOTIFY) should_sync = handle_notification(d, slot, sender);
+        a = update_node(receiver, d, clock - (int32_t)d.f[F_STARTUP]);
+        // next UpdateTimerEvent, simulator.rs:311-324
+        int64_t from_node = a.next == NODE_TIME_NEVER ? (int64_t)0x7fffffff : (int64_t)a.next + (int32_t)d.f[F_STARTUP];
+        int64_t nt = from_node > (int64_t)clock + 1 ? from_node : (int64_t)clock + 1;
+        if (nt > 0x7ffffff0) nt = 0x7ffffff0;
+        d.f[F_IGNORE] = (uint32_t)((int32_t)nt - 1);
+      }
+      // All the network sends of this event go through ONE copy of the sampling + enqueue code, in the
+      // reference's RNG order: [response | sync request] -> shuffle(receivers), notifications ->
+      // shuffle(senders), requests (simulator.rs:427-433, 448-452, 326-377).  The sync request is drawn
+      // BEFORE the timer gets its stamp in the reference?  No: process_node_actions pushes the timer first
+      // only for its own stamp; the sync request is scheduled before process_node_actions (:427-433), so
+      // its delay and stamp come first, then the timer's stamp, then the fan-out.
+      AuthorList<(NMAX <= 16 ? 16 : 64)> list;
+#pragma unroll 1
+      for (int phase = 0; phase < 3; phase++) {
+        uint32_t ev_kind, pslot = PAY_NONE;
+        list.clear();
+        if (phase == 0) {
+          ev_kind = is_request ? EV_RESPONSE : EV_REQUEST;
+          if (is_request || should_sync) list.push(sender);
+        } else if (phase == 1) {
+          if (is_request) break;
+          push_timer(receiver, d, (int32_t)d.f[F_IGNORE] + 1);  // stamp order: after the sync request, before the fan-out
+          ev_kind = EV_NOTIFY;
+          if (a.broadcast) list.fill_others(N, receiver);
+          else if (a.send_to >= 0 && (uint32_t)a.send_to != receiver) list.push((uint32_t)a.send_to);
+        } else {
+          ev_kind = EV_REQUEST;
+          if (a.query_all) list.fill_others(N, receiver);
+        }
+        for (uint32_t i = list.len; i-- > 1;) list.swap(i, gen_range_u32(i + 1));  // SliceRandom::shuffle
+        if (list.len == 0) continue;
+        if (phase == 1) {
+          pslot = pay_alloc();
+          sched_notify += list.len;
+        }
+        uint32_t queued = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < list.len; i++) {
+          uint32_t other = list.get(i);
+          // notifications travel to `other`; requests/responses are addressed to the node itself
+          uint32_t ev_recv = phase == 1 ? other : receiver, ev_send = phase == 1 ? receiver : other;
+          if (schedule_network_event(ev_kind, ev_recv, ev_send, pslot)) queued++;
+        }
+        if (phase == 1 && pslot != PAY_NONE) {
+          if (queued) write_notification(receiver, d, pslot, queued);
+          else pay_release(pslot);
+        }
+      }
+      if (!is_request) store_node(d);
     }
     if (!(status & ST_FATAL)) status |= ST_DONE;
   }

@@ -12,12 +12,12 @@
 using namespace lbft;
 static thread_local std::string g_err;
 
-template <int NMAX, bool QSCAN>
+template <int NMAX, bool QSCAN, int RW>
 static void run_all(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
-    Core<TileMem<32>, NMAX, QSCAN> core(P, mem, zx, zf);
+    Core<TileMem<32>, NMAX, QSCAN, RW> core(P, mem, zx, zf);
     core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);
@@ -26,6 +26,20 @@ static void run_all(const Params& P, std::vector<uint32_t>& state, const double*
 
 extern "C" {
 const char* hostcore_last_error(void) { return g_err.c_str(); }
+
+// What the host setup decided for a configuration: [0] delay_kmax (0 = exp() fallback), [1] scan queue,
+// [2] round_cap, [3] queue_cap, [4] payload_cap, [5] words per instance.
+int hostcore_setup_info(const lbft_config* c, uint32_t* out6) {
+  HostSetup hs;
+  if (!hs.build(*c)) { g_err = hs.error; return LBFT_ERR_INVALID; }
+  out6[0] = hs.params.delay_kmax;
+  out6[1] = hs.params.L.queue_scan;
+  out6[2] = hs.params.L.round_cap;
+  out6[3] = hs.params.L.queue_cap;
+  out6[4] = hs.params.L.payload_cap;
+  out6[5] = hs.params.L.total_words;
+  return LBFT_OK;
+}
 
 // Same outputs as the product's lbft_* getters; chain_out (optional) receives, per instance,
 // round_cap * 2 words of the chain table and leader_out (optional) the leader table.
@@ -51,10 +65,17 @@ int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_s
   P.out_counters = counters;
   P.out_status = status;
   if (words_per_instance) *words_per_instance = P.L.total_words;
-  if (P.L.queue_scan) run_all<16, true>(P, state, P.zig_x, P.zig_f);
-  else if (c->num_nodes <= 16) run_all<16, false>(P, state, P.zig_x, P.zig_f);
-  else if (c->num_nodes <= 32) run_all<32, false>(P, state, P.zig_x, P.zig_f);
-  else run_all<64, false>(P, state, P.zig_x, P.zig_f);
+  const bool rw4 = P.L.rset_words == 4;
+#define RUN(NMAX, QS)                                                  \
+  do {                                                                 \
+    if (rw4) run_all<NMAX, QS, 4>(P, state, P.zig_x, P.zig_f);         \
+    else run_all<NMAX, QS, 0>(P, state, P.zig_x, P.zig_f);             \
+  } while (0)
+  if (P.L.queue_scan) RUN(16, true);
+  else if (c->num_nodes <= 16) RUN(16, false);
+  else if (c->num_nodes <= 32) RUN(32, false);
+  else RUN(64, false);
+#undef RUN
   return LBFT_OK;
 }
 }

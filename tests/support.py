@@ -120,6 +120,14 @@ class HostCore:
         self.lib.hostcore_last_error.restype = ctypes.c_char_p
         self.lib.hostcore_run.argtypes = [ctypes.POINTER(LbftConfig), P, P, P, P, P, ctypes.POINTER(ctypes.c_uint32)]
 
+    def setup_info(self, num_nodes, max_clock=1000, **kw):
+        cfg, keep = make_config([1], num_nodes, max_clock, **kw)
+        out = np.zeros(6, np.uint32)
+        rc = self.lib.hostcore_setup_info(ctypes.byref(cfg), P(out.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(self.lib.hostcore_last_error().decode())
+        return dict(zip(("delay_kmax", "queue_scan", "round_cap", "queue_cap", "payload_cap", "words"), out.tolist()))
+
     def run(self, seeds, num_nodes, max_clock=1000, **kw):
         cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
         I = cfg.num_instances

@@ -54,3 +54,25 @@ def test_round_overflow_is_flagged(hostcore):
 def test_queue_overflow_is_flagged(hostcore):
     r = hostcore.run([9], 8, 1000, queue_cap=16, round_cap=0)
     assert r.status[0] & (4 | 2 | 8)
+
+
+def test_fast_paths_are_selected_for_the_benchmark_config(hostcore):
+    # BASELINE config 3 (N=4, LogNormal(10,4), max_clock=1000) must run on the exact delay-threshold table
+    # (no device exp), the scan queue and register-resident round bitsets (round_cap == 128)
+    info = hostcore.setup_info(4, 1000)
+    assert info["delay_kmax"] > 100 and info["queue_scan"] == 1 and info["round_cap"] == 128
+    assert hostcore.setup_info(4, 1000, delay_variance=0.0)["delay_kmax"] == 0      # constant delay: host-evaluated
+    assert hostcore.setup_info(16, 1000)["queue_scan"] == 0                         # big committees: heap
+    assert hostcore.setup_info(4, 4000)["round_cap"] > 128                          # long horizon: bitsets in memory
+
+
+def test_delay_table_equals_libm_exp_path(oracle, hostcore):
+    # wider LogNormal (sigma ~ 0.35): ~2000 thresholds; results must still equal the oracle's exp()
+    seeds = np.arange(900, 916, dtype=np.uint64)
+    kw = {"delay_mean": 15.0, "delay_variance": 30.0}
+    assert hostcore.setup_info(4, 1000, **kw)["delay_kmax"] > 1000
+    assert_same(oracle.run(seeds, 4, 1000, **kw), hostcore.run(seeds, 4, 1000, **kw))
+    kw = {"delay_mean": 25.0, "delay_variance": 200.0}  # too wide for a table -> exp() fallback path
+    assert hostcore.setup_info(4, 1000, **kw)["delay_kmax"] == 0
+    o, h = oracle.run(seeds, 4, 1500, **kw), hostcore.run(seeds, 4, 1500, **kw)
+    assert_same(o, h)
