@@ -131,7 +131,7 @@ struct HostSetup {
     // capacities
     uint32_t rcap = c.round_cap ? c.round_cap : (uint32_t)(c.max_clock / 12 + 40);
     rcap = (rcap + 31) / 32 * 32;
-    if (rcap < 128) rcap = 128;  // <= 128 rounds: the kernel keeps the per-round bitsets in registers (4 words each)
+    if (rcap < 32) rcap = 32;
     if (rcap > 32768) return fail("round_cap must be <= 32768");
     // Small committees use the scan queue (64-bit entries: time:24 | 3-kind:2 | stamp:22 | slot:8 | sender:4 |
     // receiver:4, O(1) append, linear min-scan); larger ones the binary heap with 3-word entries.
