@@ -49,6 +49,32 @@ def algorithmic_bytes(counters, n_nodes):
     return p * (2 * s_node + s_hdr) + p_notify * s_notif + q * s_hdr + q_notify * s_notif
 
 
+def effective_cores():
+    """Host threads we can actually use: CPU affinity capped by the cgroup CPU quota (the GPU boxes expose 128
+    logical CPUs but grant 16 CPUs of quota; oversubscribing only adds throttling)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def ncu_traffic_bytes(per_gpu):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the event-loop kernel, from the committed ncu
+    --set full capture of this very command (profiles/traffic.json); None if the workload differs."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if t.get("instances") == per_gpu and t.get("nodes") == NODES and t.get("max_clock") == MAX_CLOCK:
+            return t["dram_bytes_per_launch"], t.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -123,7 +149,7 @@ def cpu_baseline(per_gpu, target_seconds=12.0):
     """Time the CPU oracle on a bounded sample of the same workload, all host threads."""
     from tests.support import Oracle
     oracle = Oracle()
-    threads = os.cpu_count() or 1
+    threads = effective_cores()
     probe = step_seeds(0, 0, per_gpu)[: 64 * threads]
     r, dt, _ = run_cpu_sample(oracle, probe, threads)
     per_inst = dt / len(probe)
@@ -142,7 +168,7 @@ def run_reference_arm(args, rank, world):
         return
     from tests.support import Oracle
     oracle = Oracle()
-    threads = os.cpu_count() or 1
+    threads = effective_cores()
     per_gpu = args.instances
     # bounded sample per step so that the whole run ends within minutes
     probe = step_seeds(0, 0, per_gpu)[: 32 * threads]
@@ -285,6 +311,7 @@ def main():
         bytes_launch = algorithmic_bytes(counters_last, NODES)
         k_ms = float(np.mean(kernel_ms))
         achieved = bytes_launch / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic_bytes(per_gpu)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -298,8 +325,9 @@ def main():
             "e2e": {"value": e2e_rounds / e2e_seconds, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": 1e3 * e2e_seconds / args.steps},
             "gpu_launches": args.steps * 2,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "lbft_event_loop_kernel<16>", "kernel_ms": k_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "lbft_event_loop_kernel<16,true,0>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": bytes_launch,
                          "events_per_s": events_last / (k_ms * 1e-3)},
             "clocks": clocks,
