@@ -36,6 +36,9 @@ constexpr int kBlockThreads = 32;
 
 template <int NMAX, bool QSCAN, int RW>
 __global__ void __launch_bounds__(kBlockThreads) lbft_event_loop_kernel(const __grid_constant__ Params P) {
+  // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
+  // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
+  // measured 1.5x slower for the whole kernel (44.1 vs 28.9 ms).
   __shared__ double s_zx[257];
   __shared__ double s_zf[257];
   for (int i = threadIdx.x; i < 257; i += blockDim.x) {
