@@ -74,7 +74,7 @@ typedef struct lbft_instance_counters {
   uint32_t max_queue;         /* high-water mark of the device event queue (implementation-specific)   */
   uint32_t scheduled_notify;  /* DataSyncNotifyEvents handed a creation stamp (simulator.rs:348-354)    */
   uint32_t max_payloads;      /* high-water mark of in-flight notification snapshots (implementation)   */
-  uint32_t reserved;
+  uint32_t timers_elided;     /* duplicate timers accounted as cancelled without being queued (impl.)  */
 } lbft_instance_counters;
 
 /* Device timing of the last lbft_run / lbft_run_device, measured with CUDA events on the stream the

@@ -33,24 +33,29 @@ static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter 
 // Block = 1 warp so that the 2048 tiles of a 65 536-instance batch spread evenly over 148 SMs.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 32;
+constexpr uint32_t kThrSmem = 256;  // doubles
 
-template <int NMAX, bool QSCAN, int RW>
-__global__ void __launch_bounds__(kBlockThreads) lbft_event_loop_kernel(const __grid_constant__ Params P) {
+template <int NMAX, bool QSCAN>
+__global__ void __launch_bounds__(kBlockThreads, 14) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
   // measured 1.5x slower for the whole kernel (44.1 vs 28.9 ms).
   __shared__ double s_zx[257];
   __shared__ double s_zf[257];
+  __shared__ double s_thr[kThrSmem];  // delay thresholds (same scattered access pattern), when they fit
   for (int i = threadIdx.x; i < 257; i += blockDim.x) {
     s_zx[i] = P.zig_x[i];
     s_zf[i] = P.zig_f[i];
   }
+  const bool thr_fits = P.delay_kmax != 0 && P.delay_kmax + 2 <= kThrSmem;
+  if (thr_fits)
+    for (uint32_t i = threadIdx.x; i < P.delay_kmax + 2; i += blockDim.x) s_thr[i] = P.delay_thr[i];
   __syncthreads();
   const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= P.num_instances) return;
   const uint32_t tile = inst >> 5, lane = inst & 31;
   TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32, lane};
-  Core<TileMem<32>, NMAX, QSCAN, RW> core(P, mem, s_zx, s_zf);
+  Core<TileMem<32>, NMAX, QSCAN> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr);
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
@@ -261,9 +266,7 @@ int lbft_run_device(lbft_sim* s) {
   CUDA_TRY(cudaSetDevice(s->device));
   const uint32_t blocks = (s->I + kBlockThreads - 1) / kBlockThreads;
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
-  // (RW = 0: the per-round bitsets stay in memory.  Holding them in registers (RW = 4) was measured 38 % slower
-  // on B200: with ~14 resident warps per SM the register budget is ~128 per thread and the 12 extra words spill.)
-#define LBFT_LAUNCH(NMAX, QS) lbft_event_loop_kernel<NMAX, QS, 0><<<blocks, kBlockThreads, 0, s->stream>>>(s->P)
+#define LBFT_LAUNCH(NMAX, QS) lbft_event_loop_kernel<NMAX, QS><<<blocks, kBlockThreads, 0, s->stream>>>(s->P)
   if (s->P.L.queue_scan) LBFT_LAUNCH(16, true);
   else if (s->N <= 16) LBFT_LAUNCH(16, false);
   else if (s->N <= 32) LBFT_LAUNCH(32, false);

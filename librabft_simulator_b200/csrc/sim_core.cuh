@@ -24,7 +24,7 @@
 // (simulator.rs:446), which makes the response a no-op for the record store.
 //
 // Shape of the hot loop (what the SIMT hardware wants): one event per iteration; the receiving node's
-// whole state (scalars, author masks and — for round_cap <= 128 — the three round bitsets) is pulled
+// state (scalars, author masks and the 32-round window of the three per-round bitsets) is pulled
 // into registers with ONE batch of independent coalesced loads, updated by branch-light code, and
 // written back once; every network send of the iteration goes through ONE copy of the delay-sampling +
 // enqueue code; the rare ziggurat wedge/tail and the exp() fallback live out of line.
@@ -245,8 +245,7 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
   return flag | (int64_t)v;
 }
 
-// RW = number of 32-bit words of each per-round bitset held in registers (0: bitsets stay in memory).
-template <class Mem, int NMAX, bool QSCAN, int RW>
+template <class Mem, int NMAX, bool QSCAN>
 struct Core {
   static constexpr int S = Mem::STRIDE;
   const Params& P;
@@ -254,6 +253,7 @@ struct Core {
   Mem m;
   const double* zx;
   const double* zf;
+  const double* thr;  // delay thresholds (shared-memory copy on the device when it fits)
   // ---- per-instance registers ----
   uint64_t s0, s1, s2, s3;  // Xoshiro256** (simulator.rs:32)
   uint32_t draws;
@@ -262,9 +262,12 @@ struct Core {
   uint32_t status;
   int32_t clock;  // Simulator.clock
   uint32_t pay_free, pay_next;
-  uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify;
+  uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify, dedup;
+  uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
+  uint32_t cc0, cc1, cc2, cc3;  // chain cache: (round << 16) | previous QC round
 
-  LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_) : P(p), L(p.L), m(mem), zx(zx_), zf(zf_) {}
+  LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_)
+      : P(p), L(p.L), m(mem), zx(zx_), zf(zf_), thr(thr_) {}
 
   // ------------------------------------------------------------------------------------------
   // RNG (rand_xoshiro 0.6.0 / rand 0.8.3 / rand_distr 0.4.0)
@@ -326,7 +329,6 @@ struct Core {
       float g = expf((float)P.mu + (float)P.sigma * (float)z);
       int32_t k = g < (float)P.delay_kmax ? (int32_t)g : (int32_t)P.delay_kmax;
       if (k < 0) k = 0;
-      const double* thr = P.delay_thr;
       while (z >= thr[k + 1]) k++;
       while (z < thr[k]) k--;
       return k;
@@ -358,17 +360,32 @@ struct Core {
   }
   LBFT_HD bool mbit_test(uint32_t w, uint32_t r) const { return (m.ld(w + (r >> 5)) >> (r & 31)) & 1u; }
   LBFT_HD void mbit_set(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) | (1u << (r & 31))); }
-  LBFT_HD uint32_t chain_prev(uint32_t r) const { return m.ld(L.chain_base + 2 * r) & 0xffffu; }
+  // previous-QC round of block r.  The last few proposals of the instance are kept in a 4-entry direct-mapped
+  // register cache (written through at propose time), which serves nearly every lookup without a dependent load.
+  LBFT_HD uint32_t chain_prev(uint32_t r) const {
+    uint32_t e = (r & 2) ? ((r & 1) ? cc3 : cc2) : ((r & 1) ? cc1 : cc0);
+    if ((e >> 16) == r) return e & 0xffffu;
+    return m.ld(L.chain_base + 2 * r) & 0xffffu;
+  }
+  LBFT_HD void chain_cache_put(uint32_t r, uint32_t prev) {
+    uint32_t e = (r << 16) | prev;
+    if ((r & 3) == 0) cc0 = e;
+    if ((r & 3) == 1) cc1 = e;
+    if ((r & 3) == 2) cc2 = e;
+    if ((r & 3) == 3) cc3 = e;
+  }
 
-  // The receiving node's state, held in registers for the duration of one event.
+  // The receiving node's state, held in registers for the duration of one event.  Of the three per-round bitsets
+  // only the 32-round word around the node's current round is cached (cw); other words go to memory.
   struct NodeRegs {
     uint32_t f[F_NSCALAR];
     uint64_t vmask, tmask, tcmask;  // current_votes / current_timeouts / highest TC author sets
-    uint32_t hb[RW ? RW : 1], hq[RW ? RW : 1], pd[RW ? RW : 1];  // block known / QC known / state pending, by round
-    uint32_t* nb;  // this node's block in the tile
-    bool bits_dirty;
+    uint32_t cw;                    // index of the cached bitset word
+    uint32_t chb, chq, cpd;         // cached words: block known / QC known / state pending
+    uint32_t dirty;                 // bit0 chb, bit1 chq, bit2 cpd modified
+    uint32_t* nb;                   // this node's block in the tile
   };
-  LBFT_HD void load_node(uint32_t n, NodeRegs& d) const {
+  LBFT_HD void load_node(uint32_t n, NodeRegs& d) {
     uint32_t* nb = m.at(nbase(n));
     d.nb = nb;
 #pragma unroll
@@ -376,15 +393,19 @@ struct Core {
     d.vmask = ld_mask(nb + L.n_vmask * S);
     d.tmask = ld_mask(nb + L.n_tmask * S);
     d.tcmask = ld_mask(nb + L.n_tcmask * S);
-    if (RW) {
-#pragma unroll
-      for (int i = 0; i < (RW ? RW : 1); i++) {
-        d.hb[i] = nb[(L.n_hasblk + i) * S];
-        d.hq[i] = nb[(L.n_hasqc + i) * S];
-        d.pd[i] = nb[(L.n_pend + i) * S];
-      }
+    // speculate that this node is in the same 32-round window as the last one handled (same batch of loads)
+    d.chb = nb[(L.n_hasblk + win) * S];
+    d.chq = nb[(L.n_hasqc + win) * S];
+    d.cpd = nb[(L.n_pend + win) * S];
+    uint32_t want = d.f[F_CUR] >> 5;
+    if (want != win) {
+      d.chb = nb[(L.n_hasblk + want) * S];
+      d.chq = nb[(L.n_hasqc + want) * S];
+      d.cpd = nb[(L.n_pend + want) * S];
+      win = want;
     }
-    d.bits_dirty = false;
+    d.cw = want;
+    d.dirty = 0;
   }
   LBFT_HD void store_node(const NodeRegs& d) const {
     uint32_t* nb = d.nb;
@@ -393,39 +414,29 @@ struct Core {
     st_mask(nb + L.n_vmask * S, d.vmask);
     st_mask(nb + L.n_tmask * S, d.tmask);
     st_mask(nb + L.n_tcmask * S, d.tcmask);
-    if (RW && d.bits_dirty) {
-#pragma unroll
-      for (int i = 0; i < (RW ? RW : 1); i++) {
-        nb[(L.n_hasblk + i) * S] = d.hb[i];
-        nb[(L.n_hasqc + i) * S] = d.hq[i];
-        nb[(L.n_pend + i) * S] = d.pd[i];
-      }
+    if (d.dirty & 1) nb[(L.n_hasblk + d.cw) * S] = d.chb;
+    if (d.dirty & 2) nb[(L.n_hasqc + d.cw) * S] = d.chq;
+    if (d.dirty & 4) nb[(L.n_pend + d.cw) * S] = d.cpd;
+  }
+  LBFT_HD uint32_t bword(const NodeRegs& d, uint32_t base, uint32_t cached, uint32_t r) const {
+    return (r >> 5) == d.cw ? cached : d.nb[(base + (r >> 5)) * S];
+  }
+  LBFT_HD bool has_blk(const NodeRegs& d, uint32_t r) const { return (bword(d, L.n_hasblk, d.chb, r) >> (r & 31)) & 1u; }
+  LBFT_HD bool has_qc(const NodeRegs& d, uint32_t r) const { return (bword(d, L.n_hasqc, d.chq, r) >> (r & 31)) & 1u; }
+  LBFT_HD bool is_pend(const NodeRegs& d, uint32_t r) const { return (bword(d, L.n_pend, d.cpd, r) >> (r & 31)) & 1u; }
+  LBFT_HD void bput(NodeRegs& d, uint32_t base, uint32_t& cached, uint32_t dirty_bit, uint32_t r, bool on) const {
+    uint32_t bit = 1u << (r & 31);
+    if ((r >> 5) == d.cw) {
+      cached = on ? (cached | bit) : (cached & ~bit);
+      d.dirty |= dirty_bit;
+    } else {
+      uint32_t* p = d.nb + (base + (r >> 5)) * S;
+      *p = on ? (*p | bit) : (*p & ~bit);
     }
   }
-  // round-bitset accessors: registers when RW > 0, memory otherwise
-  LBFT_HD static bool rget(const uint32_t (&a)[RW ? RW : 1], uint32_t r) {
-    uint32_t w = a[0];
-#pragma unroll
-    for (int i = 1; i < (RW ? RW : 1); i++) w = ((r >> 5) == (uint32_t)i) ? a[i] : w;
-    return (w >> (r & 31)) & 1u;
-  }
-  LBFT_HD static void rput(uint32_t (&a)[RW ? RW : 1], uint32_t r, bool on) {
-    uint32_t bit = 1u << (r & 31);
-#pragma unroll
-    for (int i = 0; i < (RW ? RW : 1); i++)
-      if ((r >> 5) == (uint32_t)i) a[i] = on ? (a[i] | bit) : (a[i] & ~bit);
-  }
-  LBFT_HD bool has_blk(const NodeRegs& d, uint32_t r) const { return RW ? rget(d.hb, r) : ((d.nb[(L.n_hasblk + (r >> 5)) * S] >> (r & 31)) & 1u); }
-  LBFT_HD bool has_qc(const NodeRegs& d, uint32_t r) const { return RW ? rget(d.hq, r) : ((d.nb[(L.n_hasqc + (r >> 5)) * S] >> (r & 31)) & 1u); }
-  LBFT_HD bool is_pend(const NodeRegs& d, uint32_t r) const { return RW ? rget(d.pd, r) : ((d.nb[(L.n_pend + (r >> 5)) * S] >> (r & 31)) & 1u); }
-  LBFT_HD void mem_put(NodeRegs& d, uint32_t base, uint32_t r, bool on) const {
-    uint32_t* p = d.nb + (base + (r >> 5)) * S;
-    uint32_t bit = 1u << (r & 31);
-    *p = on ? (*p | bit) : (*p & ~bit);
-  }
-  LBFT_HD void set_blk(NodeRegs& d, uint32_t r) const { if (RW) { rput(d.hb, r, true); d.bits_dirty = true; } else mem_put(d, L.n_hasblk, r, true); }
-  LBFT_HD void set_qc(NodeRegs& d, uint32_t r) const { if (RW) { rput(d.hq, r, true); d.bits_dirty = true; } else mem_put(d, L.n_hasqc, r, true); }
-  LBFT_HD void set_pend(NodeRegs& d, uint32_t r, bool on) const { if (RW) { rput(d.pd, r, on); d.bits_dirty = true; } else mem_put(d, L.n_pend, r, on); }
+  LBFT_HD void set_blk(NodeRegs& d, uint32_t r) const { bput(d, L.n_hasblk, d.chb, 1u, r, true); }
+  LBFT_HD void set_qc(NodeRegs& d, uint32_t r) const { bput(d, L.n_hasqc, d.chq, 2u, r, true); }
+  LBFT_HD void set_pend(NodeRegs& d, uint32_t r, bool on) const { bput(d, L.n_pend, d.cpd, 4u, r, on); }
 
   LBFT_HD static uint32_t election(const NodeRegs& d) { return (d.f[F_FLAGS] & FL_ELECTION_MASK) >> FL_ELECTION_SHIFT; }
   LBFT_HD static void set_election(NodeRegs& d, uint32_t e) { d.f[F_FLAGS] = (d.f[F_FLAGS] & ~FL_ELECTION_MASK) | (e << FL_ELECTION_SHIFT); }
@@ -641,6 +652,7 @@ struct Core {
     mbit_set(L.created_base, r);
     m.st(L.chain_base + 2 * r, prev_round | (idx << 16));
     m.st(L.chain_base + 2 * r + 1, (uint32_t)clk);
+    chain_cache_put(r, prev_round);
     insert_block(d, r);
   }
   // create_vote :676-700
@@ -780,10 +792,11 @@ struct Core {
     pb[2 * S] = refs | ((vote | (prop << 1)) << 16);
     st_mask(pb + L.p_tcmask * S, has_tc ? d.tcmask : 0);
     st_mask(pb + L.p_curmask * S, d.tmask);
-    for (uint32_t i = 0; i < L.hcbr_words; i++) {
-      pb[(L.p_tchcbr + i) * S] = d.nb[(L.n_tchcbr + i) * S];
-      pb[(L.p_curhcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
-    }
+    // receivers read a timeout's highest_certified_block_round only for authors in the masks
+    if (has_tc)
+      for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_tchcbr + i) * S] = d.nb[(L.n_tchcbr + i) * S];
+    if (d.tmask)
+      for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_curhcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
   }
   // DataSyncNode::handle_notification (data_sync.rs:113-177).  Returns should_sync.
   LBFT_HD bool handle_notification(NodeRegs& d, uint32_t slot, uint32_t sender) {
@@ -850,7 +863,7 @@ struct Core {
       // ignore_scheduled_updates_until (simulator.rs:403-410) with no side effect: account for it
       // as popped+cancelled now and do not queue it.
       stamp++;
-      if (t <= P.max_clock) { proc3++; cancelled++; }
+      if (t <= P.max_clock) { proc3++; cancelled++; dedup++; }
       return;
     }
     d.f[F_LAST_TIMER] = (uint32_t)t;
@@ -865,7 +878,9 @@ struct Core {
     seed_rng(seed, s0, s1, s2, s3);
     draws = 0; stamp = 0; qsize = 0; status = 0; clock = 0;
     pay_free = PAY_NONE; pay_next = 0;
-    proc0 = proc1 = proc2 = proc3 = cancelled = max_queue = sched_notify = 0;
+    proc0 = proc1 = proc2 = proc3 = cancelled = max_queue = sched_notify = dedup = 0;
+    win = 0;
+    cc0 = cc1 = cc2 = cc3 = 0;
     for (uint32_t w = 0; w < N * L.node_words; w++) m.st(L.node_base + w, 0);
     for (uint32_t w = 0; w < 2 * L.rset_words; w++) m.st(L.created_base + w, 0);
     // EXTENSION D.3: partition plan from a separate stream; must match oracle_capi.cpp make_partition_plan
@@ -1029,7 +1044,7 @@ struct Core {
     uint32_t* c = P.out_counters + (size_t)inst * 12;
     c[0] = proc0; c[1] = proc1; c[2] = proc2; c[3] = proc3;
     c[4] = cancelled; c[5] = stamp; c[6] = max_round; c[7] = draws; c[8] = max_queue;
-    c[9] = sched_notify; c[10] = pay_next; c[11] = 0;
+    c[9] = sched_notify; c[10] = pay_next; c[11] = dedup;
     P.out_status[inst] = status;
   }
 };

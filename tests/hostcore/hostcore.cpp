@@ -12,12 +12,12 @@
 using namespace lbft;
 static thread_local std::string g_err;
 
-template <int NMAX, bool QSCAN, int RW>
+template <int NMAX, bool QSCAN>
 static void run_all(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
-    Core<TileMem<32>, NMAX, QSCAN, RW> core(P, mem, zx, zf);
+    Core<TileMem<32>, NMAX, QSCAN> core(P, mem, zx, zf, P.delay_thr);
     core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);
@@ -65,12 +65,7 @@ int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_s
   P.out_counters = counters;
   P.out_status = status;
   if (words_per_instance) *words_per_instance = P.L.total_words;
-  const bool rw4 = P.L.rset_words == 4;
-#define RUN(NMAX, QS)                                                  \
-  do {                                                                 \
-    if (rw4) run_all<NMAX, QS, 4>(P, state, P.zig_x, P.zig_f);         \
-    else run_all<NMAX, QS, 0>(P, state, P.zig_x, P.zig_f);             \
-  } while (0)
+#define RUN(NMAX, QS) run_all<NMAX, QS>(P, state, P.zig_x, P.zig_f)
   if (P.L.queue_scan) RUN(16, true);
   else if (c->num_nodes <= 16) RUN(16, false);
   else if (c->num_nodes <= 32) RUN(32, false);
