@@ -144,6 +144,8 @@ struct HostSetup {
     if (qcap > (1u << 20)) return fail("queue_cap too large");
     uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 4 ? 32u : (N <= 8 ? 64u : pow2_ceil(N * N)));
     if (pcap > 0xfff0u) return fail("payload_cap must be < 65520");
+    // shortest horizons: 32-bit keys (time:14 | kind:2 | stamp:16) + 16-bit payload words, queue in shared memory
+    if (qscan && c.max_clock < (1 << 14) - 64 && qcap <= 64 && pcap <= 255) qscan = 2;
     p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan);
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
     leader.resize(rcap + 1);

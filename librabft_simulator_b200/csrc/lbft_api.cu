@@ -35,14 +35,25 @@ static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter 
 constexpr int kBlockThreads = 32;
 constexpr uint32_t kThrSmem = 256;  // doubles
 
-template <int NMAX, bool QSCAN>
-__global__ void __launch_bounds__(kBlockThreads, 14) lbft_event_loop_kernel(const __grid_constant__ Params P) {
+// Launch shapes.  QMODE 0/1: one-warp blocks, 14 resident per SM (2 048 tiles of a 65 536-instance batch over 148
+// SMs; <= 144 registers/thread keeps every tile resident).  QMODE 2: two-warp blocks, 7 per SM, so that the
+// ziggurat/threshold tables (6 KB) are shared by two tiles and the per-tile event queues (queue_cap x 32 x 6 B)
+// fit in the 227 KB of shared memory.
+template <int QMODE>
+struct LaunchShape {
+  static constexpr int kThreads = QMODE == 2 ? 64 : 32;
+  static constexpr int kBlocksPerSm = QMODE == 2 ? 7 : 14;
+};
+
+template <int NMAX, int QMODE>
+__global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
   // measured 1.5x slower for the whole kernel (44.1 vs 28.9 ms).
   __shared__ double s_zx[257];
   __shared__ double s_zf[257];
   __shared__ double s_thr[kThrSmem];  // delay thresholds (same scattered access pattern), when they fit
+  extern __shared__ uint32_t s_queue[];  // QMODE 2: per warp [queue_cap][32] u32 keys, then [queue_cap][32] u16 payload words
   for (int i = threadIdx.x; i < 257; i += blockDim.x) {
     s_zx[i] = P.zig_x[i];
     s_zf[i] = P.zig_f[i];
@@ -55,7 +66,15 @@ __global__ void __launch_bounds__(kBlockThreads, 14) lbft_event_loop_kernel(cons
   if (inst >= P.num_instances) return;
   const uint32_t tile = inst >> 5, lane = inst & 31;
   TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32, lane};
-  Core<TileMem<32>, NMAX, QSCAN> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr);
+  uint32_t* sk = nullptr;
+  uint16_t* sd = nullptr;
+  if (QMODE == 2) {
+    const uint32_t warp = threadIdx.x >> 5, qcap = P.L.queue_cap;
+    uint32_t* base = s_queue + (size_t)warp * (qcap * 32 + qcap * 16);  // keys (qcap*32 words) + payload (qcap*32 halves)
+    sk = base + lane;
+    sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
+  }
+  Core<TileMem<32>, NMAX, QMODE> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
@@ -264,13 +283,19 @@ int lbft_run_device(lbft_sim* s) {
   if (!s) return set_error(LBFT_ERR_INVALID, "sim must not be NULL");
   if (!s->uploaded) return set_error(LBFT_ERR_STATE, "lbft_upload must be called before lbft_run_device");
   CUDA_TRY(cudaSetDevice(s->device));
-  const uint32_t blocks = (s->I + kBlockThreads - 1) / kBlockThreads;
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
-#define LBFT_LAUNCH(NMAX, QS) lbft_event_loop_kernel<NMAX, QS><<<blocks, kBlockThreads, 0, s->stream>>>(s->P)
-  if (s->P.L.queue_scan) LBFT_LAUNCH(16, true);
-  else if (s->N <= 16) LBFT_LAUNCH(16, false);
-  else if (s->N <= 32) LBFT_LAUNCH(32, false);
-  else LBFT_LAUNCH(64, false);
+#define LBFT_LAUNCH(NMAX, QM)                                                                                      \
+  do {                                                                                                             \
+    constexpr int T = LaunchShape<QM>::kThreads;                                                                   \
+    const uint32_t blocks = (s->I + T - 1) / T;                                                                    \
+    const size_t dyn = QM == 2 ? (size_t)(T / 32) * s->P.L.queue_cap * (32 * 4 + 32 * 2) : 0;                      \
+    lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, s->stream>>>(s->P);                                        \
+  } while (0)
+  if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);
+  else if (s->P.L.queue_scan == 1) LBFT_LAUNCH(16, 1);
+  else if (s->N <= 16) LBFT_LAUNCH(16, 0);
+  else if (s->N <= 32) LBFT_LAUNCH(32, 0);
+  else LBFT_LAUNCH(64, 0);
 #undef LBFT_LAUNCH
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));

@@ -245,7 +245,9 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
   return flag | (int64_t)v;
 }
 
-template <class Mem, int NMAX, bool QSCAN>
+// QMODE: 0 binary heap (3-word entries, HBM) | 1 scan queue, 64-bit keys in HBM | 2 scan queue, 32-bit keys +
+// 16-bit payload words in shared memory (small committees, short horizons)
+template <class Mem, int NMAX, int QMODE>
 struct Core {
   static constexpr int S = Mem::STRIDE;
   const Params& P;
@@ -254,6 +256,8 @@ struct Core {
   const double* zx;
   const double* zf;
   const double* thr;  // delay thresholds (shared-memory copy on the device when it fits)
+  uint32_t* sk;       // QMODE 2: this lane's key column,  sk[j * 32] = time:14 | 3-kind:2 | stamp:16
+  uint16_t* sd;       // QMODE 2: this lane's data column, sd[j * 32] = slot:8 | sender:4 | receiver:4
   // ---- per-instance registers ----
   uint64_t s0, s1, s2, s3;  // Xoshiro256** (simulator.rs:32)
   uint32_t draws;
@@ -266,8 +270,9 @@ struct Core {
   uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
   uint32_t cc0, cc1, cc2, cc3;  // chain cache: (round << 16) | previous QC round
 
-  LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_)
-      : P(p), L(p.L), m(mem), zx(zx_), zf(zf_), thr(thr_) {}
+  LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_, uint32_t* sk_ = nullptr,
+               uint16_t* sd_ = nullptr)
+      : P(p), L(p.L), m(mem), zx(zx_), zf(zf_), thr(thr_), sk(sk_), sd(sd_) {}
 
   // ------------------------------------------------------------------------------------------
   // RNG (rand_xoshiro 0.6.0 / rand 0.8.3 / rand_distr 0.4.0)
@@ -444,8 +449,8 @@ struct Core {
 
   // ------------------------------------------------------------------------------------------
   // pending-event queue, ordered by (time, 3-kind, stamp)  (simulator.rs:149-161)
-  //   QSCAN: unsorted array of 64-bit keys, O(1) append, linear min-scan on pop
-  //   else : binary min-heap with 3-word entries
+  //   QMODE 1/2: unsorted array, O(1) append, linear min-scan on pop (64-bit keys in HBM / 32-bit keys in smem)
+  //   QMODE 0  : binary min-heap with 3-word entries
   // ------------------------------------------------------------------------------------------
   LBFT_HD uint64_t heap_key_at(uint32_t i) const { return ((uint64_t)m.ld(L.heap_time + i) << 32) | m.ld(L.heap_key + i); }
   LBFT_HD void heap_move(uint32_t dst, uint32_t src) const {
@@ -458,10 +463,18 @@ struct Core {
   // `data` = receiver | sender << 8 | slot << 16.
   LBFT_HD bool push_event(int32_t time, uint32_t kind, uint32_t data) {
     uint32_t st = stamp++;
-    if (stamp >= (QSCAN ? (1u << 22) : (1u << 30))) status |= ST_QUEUE_OVERFLOW;
+    if (stamp >= (QMODE == 2 ? (1u << 16) : (QMODE == 1 ? (1u << 22) : (1u << 30)))) status |= ST_QUEUE_OVERFLOW;
     if (time > P.max_clock) return false;
     if (qsize >= L.queue_cap) { status |= ST_QUEUE_OVERFLOW; return false; }
-    if (QSCAN) {
+    if (QMODE == 2) {
+      // stamps are unique, so a 32-bit key decides every comparison; the payload word is not compared
+      sk[qsize * 32] = ((uint32_t)time << 18) | ((3u - kind) << 16) | (st & 0xffffu);
+      sd[qsize * 32] = (uint16_t)((((data >> 16) & 0xffu) << 8) | (((data >> 8) & 0xfu) << 4) | (data & 0xfu));
+      qsize++;
+      if (qsize > max_queue) max_queue = qsize;
+      return true;
+    }
+    if (QMODE == 1) {
       // key = time:24 | 3-kind:2 | stamp:22 | slot:8 | sender:4 | receiver:4; stamps are unique, so the
       // payload bits below them never decide a comparison.
       uint64_t key = ((uint64_t)(uint32_t)time << 40) | ((uint64_t)(3u - kind) << 38) | ((uint64_t)st << 16) |
@@ -487,7 +500,36 @@ struct Core {
     return true;
   }
   LBFT_HD void pop_event(int32_t& time, uint32_t& kind, uint32_t& data) {
-    if (QSCAN) {
+    if (QMODE == 2) {
+      uint32_t best = sk[0], bi = 0;
+      const uint32_t n = qsize;
+      uint32_t j = 1;
+#pragma unroll 1
+      for (; j + 3 < n; j += 4) {
+        uint32_t k0 = sk[j * 32], k1 = sk[(j + 1) * 32], k2 = sk[(j + 2) * 32], k3 = sk[(j + 3) * 32];
+        if (k0 < best) { best = k0; bi = j; }
+        if (k1 < best) { best = k1; bi = j + 1; }
+        if (k2 < best) { best = k2; bi = j + 2; }
+        if (k3 < best) { best = k3; bi = j + 3; }
+      }
+#pragma unroll 1
+      for (; j < n; j++) {
+        uint32_t k0 = sk[j * 32];
+        if (k0 < best) { best = k0; bi = j; }
+      }
+      uint32_t lo = sd[bi * 32];
+      qsize = n - 1;
+      if (bi != n - 1) {
+        sk[bi * 32] = sk[(n - 1) * 32];
+        sd[bi * 32] = sd[(n - 1) * 32];
+      }
+      time = (int32_t)(best >> 18);
+      kind = 3u - ((best >> 16) & 3u);
+      uint32_t slot = lo >> 8;
+      data = (lo & 0xfu) | (((lo >> 4) & 0xfu) << 8) | ((slot == 0xffu ? PAY_NONE : slot) << 16);
+      return;
+    }
+    if (QMODE == 1) {
       // linear min-scan: independent, fully coalesced loads; no data-dependent sift chains
       const uint64_t* q = m.at64(L.heap_time);
       uint64_t best = q[0];

@@ -59,7 +59,7 @@ struct Layout {
   uint32_t hcbr_words;   // ceil(N/2): per-author u16 highest_certified_block_round of a timeout
   uint32_t rset_words;   // round_cap/32: per-round bitsets
   uint32_t round_cap, queue_cap, payload_cap, part_windows;
-  uint32_t queue_scan;   // 1: unsorted array + linear min-scan, 64-bit entries (small N); 0: binary heap, 3-word entries
+  uint32_t queue_scan;   // 0 binary heap (3-word entries) | 1 scan queue, 64-bit entries in HBM | 2 scan queue, 32+16-bit entries in shared memory
   // word offsets inside a node block
   uint32_t n_vmask, n_tmask, n_tcmask, n_thcbr, n_tchcbr, n_hasblk, n_hasqc, n_pend, node_words;
   // word offsets inside an instance

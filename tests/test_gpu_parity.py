@@ -58,6 +58,8 @@ CASES = [
     (21, 64, 4, 1000, {"delay_mean": 25.0, "delay_variance": 200.0}),
     (31, 32, 5, 1500, {"delta": 5, "gamma": 1.5, "lambda_": 0.25, "queue_cap": 4096, "payload_cap": 1024}),
     (41, 16, 4, 4000, {"target_commit_interval": 300, "delta": 400}),
+    (61, 64, 4, 1000, {"queue_cap": 128}),   # 64-bit-key scan queue in HBM (QMODE 1)
+    (62, 40, 6, 1000, {}),                   # binary heap (QMODE 0) at small N
 ]
 
 

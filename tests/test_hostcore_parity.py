@@ -21,6 +21,8 @@ CASES = [
     (21, 16, 4, 1000, {"delay_mean": 25.0, "delay_variance": 200.0}),  # heavy jitter -> timeouts/TCs
     (31, 16, 5, 1500, {"delta": 5, "gamma": 1.5, "lambda_": 0.25, "queue_cap": 4096, "payload_cap": 1024}),   # tight pacemaker -> many timeouts, query-all
     (41, 8, 4, 4000, {"target_commit_interval": 300, "delta": 400}),  # commit tracker query-all path
+    (61, 16, 4, 1000, {"queue_cap": 128}),   # forces the 64-bit-key scan queue in HBM (QMODE 1)
+    (62, 8, 6, 1000, {}),                    # heap (QMODE 0) at small N
 ]
 
 
@@ -60,7 +62,8 @@ def test_fast_paths_are_selected_for_the_benchmark_config(hostcore):
     # BASELINE config 3 (N=4, LogNormal(10,4), max_clock=1000) must run on the exact delay-threshold table
     # (no device exp) and the scan queue
     info = hostcore.setup_info(4, 1000)
-    assert info["delay_kmax"] > 100 and info["queue_scan"] == 1 and info["round_cap"] == 128
+    assert info["delay_kmax"] > 100 and info["queue_scan"] == 2 and info["round_cap"] == 128
+    assert hostcore.setup_info(4, 20000)["queue_scan"] == 1                         # long horizon: 64-bit keys in HBM
     assert hostcore.setup_info(4, 1000, delay_variance=0.0)["delay_kmax"] == 0      # constant delay: host-evaluated
     assert hostcore.setup_info(16, 1000)["queue_scan"] == 0                         # big committees: heap
 
