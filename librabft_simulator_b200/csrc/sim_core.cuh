@@ -1004,33 +1004,44 @@ struct Core {
         if (nt > 0x7ffffff0) nt = 0x7ffffff0;
         d.f[F_IGNORE] = (uint32_t)((int32_t)nt - 1);
       }
-      // All the network sends of this event go through ONE copy of the sampling + enqueue code, in the
-      // reference's RNG order: [response | sync request] -> shuffle(receivers), notifications ->
-      // shuffle(senders), requests (simulator.rs:427-433, 448-452, 326-377).  The sync request is drawn
-      // BEFORE the timer gets its stamp in the reference?  No: process_node_actions pushes the timer first
-      // only for its own stamp; the sync request is scheduled before process_node_actions (:427-433), so
-      // its delay and stamp come first, then the timer's stamp, then the fan-out.
+      // All the network sends of this event go through ONE copy of the sampling + enqueue code, in the reference's
+      // RNG / creation-stamp order: [sync request (simulator.rs:427-433)] -> timer stamp (:311-324) ->
+      // shuffle(receivers), notifications (:326-354) -> shuffle(senders), requests (:356-377); a Request event
+      // only schedules its Response (:448-452).  The 32 instances of a warp execute the passes together, so the
+      // cost of an iteration is the number of passes x the longest list in each.  Two exact foldings keep that
+      // small: a Request event's single Response send, and a query-all fan-out whose notification list is empty,
+      // run inside the notification pass (nothing of the same instance lies between them in the RNG stream).
       AuthorList<(NMAX <= 16 ? 16 : 64)> list;
+      bool query_pending = a.query_all;
 #pragma unroll 1
       for (int phase = 0; phase < 3; phase++) {
-        uint32_t ev_kind, pslot = PAY_NONE;
+        uint32_t ev_kind = EV_REQUEST, pslot = PAY_NONE;
+        bool to_other = false;  // notifications travel to `other`; requests/responses are addressed to the node itself
         list.clear();
         if (phase == 0) {
-          ev_kind = is_request ? EV_RESPONSE : EV_REQUEST;
-          if (is_request || should_sync) list.push(sender);
+          if (should_sync) list.push(sender);
         } else if (phase == 1) {
-          if (is_request) break;
-          push_timer(receiver, d, (int32_t)d.f[F_IGNORE] + 1);  // stamp order: after the sync request, before the fan-out
-          ev_kind = EV_NOTIFY;
-          if (a.broadcast) list.fill_others(N, receiver);
-          else if (a.send_to >= 0 && (uint32_t)a.send_to != receiver) list.push((uint32_t)a.send_to);
+          if (is_request) {
+            ev_kind = EV_RESPONSE;
+            list.push(sender);
+          } else {
+            push_timer(receiver, d, (int32_t)d.f[F_IGNORE] + 1);  // its stamp comes after the sync request, before the fan-out
+            if (a.broadcast) list.fill_others(N, receiver);
+            else if (a.send_to >= 0 && (uint32_t)a.send_to != receiver) list.push((uint32_t)a.send_to);
+            if (list.len) {
+              ev_kind = EV_NOTIFY;
+              to_other = true;
+            } else if (query_pending) {
+              list.fill_others(N, receiver);
+              query_pending = false;
+            }
+          }
         } else {
-          ev_kind = EV_REQUEST;
-          if (a.query_all) list.fill_others(N, receiver);
+          if (query_pending) list.fill_others(N, receiver);
         }
         for (uint32_t i = list.len; i-- > 1;) list.swap(i, gen_range_u32(i + 1));  // SliceRandom::shuffle
         if (list.len == 0) continue;
-        if (phase == 1) {
+        if (to_other) {
           pslot = pay_alloc();
           sched_notify += list.len;
         }
@@ -1038,11 +1049,10 @@ struct Core {
 #pragma unroll 1
         for (uint32_t i = 0; i < list.len; i++) {
           uint32_t other = list.get(i);
-          // notifications travel to `other`; requests/responses are addressed to the node itself
-          uint32_t ev_recv = phase == 1 ? other : receiver, ev_send = phase == 1 ? receiver : other;
+          uint32_t ev_recv = to_other ? other : receiver, ev_send = to_other ? receiver : other;
           if (schedule_network_event(ev_kind, ev_recv, ev_send, pslot)) queued++;
         }
-        if (phase == 1 && pslot != PAY_NONE) {
+        if (to_other && pslot != PAY_NONE) {
           if (queued) write_notification(receiver, d, pslot, queued);
           else pay_release(pslot);
         }
