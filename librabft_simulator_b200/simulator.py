@@ -84,14 +84,35 @@ class SimulatedContextView:
 
 
 class BatchResult:
-    """Results of ``BatchSimulator.loop_until``: what the reference's callers read from ``Vec<&Context>``."""
+    """Results of ``BatchSimulator.loop_until``: what the reference's callers read from ``Vec<&Context>``.
+    The arrays are copied out of the library's (pinned) result buffers on first access."""
 
     def __init__(self, sim):
         self._sim = sim
-        self.commit_counts = sim._fetch_u32("lbft_commit_counts", (sim.num_instances, sim.num_nodes))
-        self.last_committed_states = sim._fetch_u64("lbft_last_states", (sim.num_instances, sim.num_nodes))
-        self.counters = sim._fetch_u32("lbft_counters", (sim.num_instances, 12))
-        self.status = sim._fetch_u32("lbft_status", (sim.num_instances,))
+        self._cache = {}
+
+    def _get(self, name, fn, dtype, shape):
+        if name not in self._cache:
+            self._cache[name] = self._sim._fetch(fn, dtype, shape)
+        return self._cache[name]
+
+    @property
+    def commit_counts(self):
+        """``committed_history().len()`` per node: [instance, node]."""
+        return self._get("cc", "lbft_commit_counts", np.uint32, (self._sim.num_instances, self._sim.num_nodes))
+
+    @property
+    def last_committed_states(self):
+        """``last_committed_state()`` per node (SipHash-1-3 key of the commit log): [instance, node]."""
+        return self._get("ls", "lbft_last_states", np.uint64, (self._sim.num_instances, self._sim.num_nodes))
+
+    @property
+    def counters(self):
+        return self._get("cnt", "lbft_counters", np.uint32, (self._sim.num_instances, 12))
+
+    @property
+    def status(self):
+        return self._get("st", "lbft_status", np.uint32, (self._sim.num_instances,))
 
     # lbft_instance_counters columns
     @property
@@ -230,13 +251,8 @@ class BatchSimulator:
         return int(b.value), int(w.value)
 
     # -- results --------------------------------------------------------------------------------
-    def _fetch_u32(self, fn, shape):
-        out = np.zeros(shape, dtype=np.uint32)
-        _lib.check(getattr(self._lib, fn)(self._handle, ctypes.c_void_p(out.ctypes.data)))
-        return out
-
-    def _fetch_u64(self, fn, shape):
-        out = np.zeros(shape, dtype=np.uint64)
+    def _fetch(self, fn, dtype, shape):
+        out = np.empty(shape, dtype=dtype)
         _lib.check(getattr(self._lib, fn)(self._handle, ctypes.c_void_p(out.ctypes.data)))
         return out
 

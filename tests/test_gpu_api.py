@@ -1,0 +1,76 @@
+"""C-ABI behaviour on a real device: call-sequence errors, re-seeding, determinism, timing/memory info and the
+device-buffer view used for the NCCL all-gather."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make(seeds, nodes=4, **kw):
+    from librabft_simulator_b200 import BatchSimulator, RandomDelay
+    return BatchSimulator(seeds, nodes, RandomDelay.new(10.0, 4.0), **kw)
+
+
+def test_results_before_run_are_an_error():
+    from librabft_simulator_b200 import _lib
+    sim = make(np.arange(1, 33, dtype=np.uint64)).create(1000)
+    out = np.zeros((32, 4), np.uint32)
+    rc = sim._lib.lbft_commit_counts(sim._handle, ctypes.c_void_p(out.ctypes.data))
+    assert rc == -3 and b"lbft_run" in sim._lib.lbft_last_error()
+    with pytest.raises(_lib.LbftError):
+        sim.run_device()          # upload must come first
+    sim.upload()
+    sim.run_device()
+    rc = sim._lib.lbft_commit_counts(sim._handle, ctypes.c_void_p(out.ctypes.data))
+    assert rc == -3               # still not downloaded
+    res = sim.download()
+    assert res.commit_counts.min() > 5
+    sim.close()
+
+
+def test_rerun_is_deterministic_and_reseeding_changes_results(oracle):
+    seeds = np.arange(700, 764, dtype=np.uint64)
+    sim = make(seeds).create(1000)
+    a = sim.run()
+    a_states = a.last_committed_states.copy()
+    b = sim.run()
+    np.testing.assert_array_equal(a_states, b.last_committed_states)
+    seeds2 = seeds + np.uint64(5000)
+    sim.set_seeds(seeds2)
+    c = sim.run()
+    assert (c.last_committed_states != a_states).any()
+    ref = oracle.run(seeds2, 4, 1000)
+    np.testing.assert_array_equal(ref.last_states, c.last_committed_states)
+    np.testing.assert_array_equal(ref.commit_counts, c.commit_counts)
+    assert sim.timing.kernel_launches == 1 and sim.timing.sim_ms > 0
+    assert sim.timing.h2d_bytes == 64 * 8 and sim.timing.d2h_bytes > 0
+    dev_bytes, words = sim.memory_info()
+    assert dev_bytes > 64 * words * 4 * 0.9 and words > 100
+    sim.close()
+
+
+def test_device_buffer_view_matches_host_results():
+    import torch
+    seeds = np.arange(40, 104, dtype=np.uint64)
+    sim = make(seeds).create(1000)
+    res = sim.run()
+    ptr, nbytes = sim.device_buffer(0)
+    assert nbytes == 64 * 4 * 4
+
+    class Cai:
+        __cuda_array_interface__ = {"shape": (64 * 4,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    t = torch.as_tensor(Cai(), device="cuda:0").cpu().numpy().astype(np.uint32).reshape(64, 4)
+    np.testing.assert_array_equal(t, res.commit_counts)
+    sim.close()
+
+
+def test_two_handles_are_independent():
+    s1 = make(np.arange(1, 33, dtype=np.uint64)).create(1000)
+    s2 = make(np.arange(1, 33, dtype=np.uint64), nodes=7).create(500)
+    r2 = s2.run()
+    r1 = s1.run()
+    assert r1.commit_counts.shape == (32, 4) and r2.commit_counts.shape == (32, 7)
+    assert r1.commit_counts.min() > 10
+    s1.close(); s2.close()

@@ -10,6 +10,15 @@ from tests.support import assert_same
 pytestmark = pytest.mark.gpu
 
 
+class GpuResult:
+    """Adapter giving the product's BatchResult the attribute names of tests.support.Result."""
+
+    def __init__(self, res):
+        self.commit_counts, self.last_states = res.commit_counts, res.last_committed_states
+        self.last_committed_states = self.last_states
+        self.counters, self.status = res.counters, res.status
+
+
 def gpu_run(seeds, nodes, max_clock=1000, strict=True, **kw):
     from librabft_simulator_b200 import BatchSimulator, NodeConfig, RandomDelay
     delay = RandomDelay.new(kw.pop("delay_mean", 10.0), kw.pop("delay_variance", 4.0))
@@ -19,8 +28,7 @@ def gpu_run(seeds, nodes, max_clock=1000, strict=True, **kw):
     nc = NodeConfig(kw.pop("target_commit_interval", 100000), kw.pop("delta", 20), kw.pop("gamma", 2.0), kw.pop("lambda_", 0.5))
     sim = BatchSimulator(seeds, nodes, delay, nc, kw.pop("commands_per_epoch", 30000), **kw)
     res = sim.loop_until(max_clock, strict=strict)
-    res.last_states = res.last_committed_states
-    return sim, res
+    return sim, GpuResult(res)
 
 
 def test_native_library_is_loaded():
