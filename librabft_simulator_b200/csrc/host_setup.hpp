@@ -142,11 +142,14 @@ struct HostSetup {
     if (2 * qcap < rcap && qscan) qcap = (rcap + 1) / 2;  // the read-out reuses the queue area as chain scratch
     if (qcap < rcap && !qscan) qcap = rcap;
     if (qcap > (1u << 20)) return fail("queue_cap too large");
-    uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 4 ? 32u : (N <= 8 ? 64u : pow2_ceil(N * N)));
+    uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 4 ? 32u : (N <= 8 ? 64u : pow2_ceil(8 * N)));
     if (pcap > 0xfff0u) return fail("payload_cap must be < 65520");
     // shortest horizons: 32-bit keys (time:14 | kind:2 | stamp:16) + 16-bit payload words, queue in shared memory
     if (qscan && c.max_clock < (1 << 14) - 64 && qcap <= 64 && pcap <= 255) qscan = 2;
-    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan);
+    // everything else with a moderate horizon: calendar queue (O(1) push/pop, exact: FIFO order inside a (time, kind)
+    // list is creation-stamp order); the binary heap remains for long horizons
+    if (qscan == 0 && c.max_clock <= 4095 && qcap <= 0xfff0u) qscan = 3;
+    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock);
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
     leader.resize(rcap + 1);
     for (uint32_t r = 0; r <= rcap; r++) leader[r] = (uint8_t)pick_author(weights, total, siphash13_u64(r));

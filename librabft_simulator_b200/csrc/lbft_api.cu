@@ -293,7 +293,11 @@ int lbft_run_device(lbft_sim* s) {
   } while (0)
   if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);
   else if (s->P.L.queue_scan == 1) LBFT_LAUNCH(16, 1);
-  else if (s->N <= 16) LBFT_LAUNCH(16, 0);
+  else if (s->P.L.queue_scan == 3) {
+    if (s->N <= 16) LBFT_LAUNCH(16, 3);
+    else if (s->N <= 32) LBFT_LAUNCH(32, 3);
+    else LBFT_LAUNCH(64, 3);
+  } else if (s->N <= 16) LBFT_LAUNCH(16, 0);
   else if (s->N <= 32) LBFT_LAUNCH(32, 0);
   else LBFT_LAUNCH(64, 0);
 #undef LBFT_LAUNCH

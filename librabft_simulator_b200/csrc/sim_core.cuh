@@ -246,7 +246,7 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 }
 
 // QMODE: 0 binary heap (3-word entries, HBM) | 1 scan queue, 64-bit keys in HBM | 2 scan queue, 32-bit keys +
-// 16-bit payload words in shared memory (small committees, short horizons)
+// 16-bit payload words in shared memory (small committees, short horizons) | 3 calendar queue in HBM
 template <class Mem, int NMAX, int QMODE>
 struct Core {
   static constexpr int S = Mem::STRIDE;
@@ -268,6 +268,7 @@ struct Core {
   uint32_t pay_free, pay_next;
   uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify, dedup;
   uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
+  uint32_t cal_t, cal_free, cal_next;  // QMODE 3: current bucket time, pool free list head, pool bump pointer
   uint32_t cc0, cc1, cc2, cc3;  // chain cache: (round << 16) | previous QC round
 
   LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_, uint32_t* sk_ = nullptr,
@@ -463,9 +464,30 @@ struct Core {
   // `data` = receiver | sender << 8 | slot << 16.
   LBFT_HD bool push_event(int32_t time, uint32_t kind, uint32_t data) {
     uint32_t st = stamp++;
-    if (stamp >= (QMODE == 2 ? (1u << 16) : (QMODE == 1 ? (1u << 22) : (1u << 30)))) status |= ST_QUEUE_OVERFLOW;
+    if (stamp >= (QMODE == 2 ? (1u << 16) : (QMODE == 1 ? (1u << 22) : (QMODE == 3 ? 0xfffffff0u : (1u << 30))))) status |= ST_QUEUE_OVERFLOW;
     if (time > P.max_clock) return false;
     if (qsize >= L.queue_cap) { status |= ST_QUEUE_OVERFLOW; return false; }
+    if (QMODE == 3) {
+      // calendar queue: one FIFO list per (time, kind).  Creation stamps grow with every push, so FIFO order inside
+      // a list IS stamp order, and the pop below takes kinds in priority order: exactly (time, kind desc, stamp).
+      uint32_t e;
+      if (cal_free != PAY_NONE) { e = cal_free; cal_free = m.ld(L.heap_time + e); }
+      else e = cal_next++;
+      m.st(L.heap_key + e, data);
+      const uint32_t t = (uint32_t)time, kw = L.cal_kmask + (t >> 3), sh = (t & 7) * 4 + kind, hw = L.cal_ht + t * 4 + kind;
+      uint32_t occ = m.ld(kw);
+      if ((occ >> sh) & 1) {
+        uint32_t ht = m.ld(hw);
+        m.st(L.heap_time + (ht >> 16), e);       // old tail -> e
+        m.st(hw, (ht & 0xffffu) | (e << 16));
+      } else {
+        m.st(hw, e | (e << 16));
+        m.st(kw, occ | (1u << sh));
+      }
+      qsize++;
+      if (qsize > max_queue) max_queue = qsize;
+      return true;
+    }
     if (QMODE == 2) {
       // stamps are unique, so a 32-bit key decides every comparison; the payload word is not compared
       sk[qsize * 32] = ((uint32_t)time << 18) | ((3u - kind) << 16) | (st & 0xffffu);
@@ -500,6 +522,29 @@ struct Core {
     return true;
   }
   LBFT_HD void pop_event(int32_t& time, uint32_t& kind, uint32_t& data) {
+    if (QMODE == 3) {
+      // advance to the first time slot with a pending list (pushes never go below the current slot)
+      uint32_t kw = L.cal_kmask + (cal_t >> 3);
+      uint32_t occ = m.ld(kw) >> ((cal_t & 7) * 4);
+      while (occ == 0) {
+        cal_t = (cal_t | 7) + 1;
+        kw++;
+        occ = m.ld(kw);
+      }
+      while ((occ & 15u) == 0) { occ >>= 4; cal_t++; }
+      const uint32_t nib = occ & 15u;
+      kind = nib & 8u ? 3u : (nib & 4u ? 2u : (nib & 2u ? 1u : 0u));  // Timer 3 > Response 2 > Request 1 > Notify 0
+      const uint32_t hw = L.cal_ht + cal_t * 4 + kind;
+      const uint32_t ht = m.ld(hw), e = ht & 0xffffu;
+      data = m.ld(L.heap_key + e);
+      if (e == (ht >> 16)) m.st(kw, m.ld(kw) & ~(1u << ((cal_t & 7) * 4 + kind)));  // list became empty
+      else m.st(hw, (ht & 0xffff0000u) | m.ld(L.heap_time + e));
+      m.st(L.heap_time + e, cal_free);
+      cal_free = e;
+      time = (int32_t)cal_t;
+      qsize--;
+      return;
+    }
     if (QMODE == 2) {
       uint32_t best = sk[0], bi = 0;
       const uint32_t n = qsize;
@@ -923,6 +968,9 @@ struct Core {
     proc0 = proc1 = proc2 = proc3 = cancelled = max_queue = sched_notify = dedup = 0;
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
+    cal_t = 0; cal_free = PAY_NONE; cal_next = 0;
+    if (QMODE == 3)
+      for (uint32_t w = 0; w < (L.cal_times + 7) / 8; w++) m.st(L.cal_kmask + w, 0);
     for (uint32_t w = 0; w < N * L.node_words; w++) m.st(L.node_base + w, 0);
     for (uint32_t w = 0; w < 2 * L.rset_words; w++) m.st(L.created_base + w, 0);
     // EXTENSION D.3: partition plan from a separate stream; must match oracle_capi.cpp make_partition_plan

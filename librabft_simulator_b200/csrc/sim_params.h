@@ -59,7 +59,9 @@ struct Layout {
   uint32_t hcbr_words;   // ceil(N/2): per-author u16 highest_certified_block_round of a timeout
   uint32_t rset_words;   // round_cap/32: per-round bitsets
   uint32_t round_cap, queue_cap, payload_cap, part_windows;
-  uint32_t queue_scan;   // 0 binary heap (3-word entries) | 1 scan queue, 64-bit entries in HBM | 2 scan queue, 32+16-bit entries in shared memory
+  uint32_t queue_scan;   // QMODE: 0 binary heap (3-word entries) | 1 scan queue, 64-bit entries in HBM | 2 scan queue, 32+16-bit
+                         // entries in shared memory | 3 calendar queue (per-(time, kind) FIFO lists) in HBM
+  uint32_t cal_kmask, cal_ht, cal_times;  // QMODE 3: kind-occupancy nibbles (8 times per word), head|tail<<16 per (time, kind)
   // word offsets inside a node block
   uint32_t n_vmask, n_tmask, n_tcmask, n_thcbr, n_tchcbr, n_hasblk, n_hasqc, n_pend, node_words;
   // word offsets inside an instance
@@ -71,7 +73,7 @@ struct Layout {
 };
 
 inline Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
-                          uint32_t queue_scan) {
+                          uint32_t queue_scan, uint32_t max_clock = 0) {
   Layout L{};
   L.queue_scan = queue_scan;
   L.num_nodes = N;
@@ -101,7 +103,12 @@ inline Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, ui
   o = (o + 1) & ~1u;  // 64-bit entries of the scan queue need an even word offset
   L.heap_time = o; o += queue_cap;
   L.heap_key = o; o += queue_cap;
-  if (!queue_scan) { L.heap_data = o; o += queue_cap; }
+  if (queue_scan == 0) { L.heap_data = o; o += queue_cap; }
+  if (queue_scan == 3) {  // heap_time = pool `next` links, heap_key = pool payload words
+    L.cal_times = max_clock + 1;
+    L.cal_kmask = o; o += (L.cal_times + 7) / 8;
+    L.cal_ht = o; o += L.cal_times * 4;
+  }
   L.p_tcmask = 3;
   L.p_curmask = L.p_tcmask + L.mask_words;
   L.p_tchcbr = L.p_curmask + L.mask_words;

@@ -70,7 +70,11 @@ int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_s
 #define RUN(NMAX, QS) run_all<NMAX, QS>(P, state, P.zig_x, P.zig_f)
   if (P.L.queue_scan == 2) RUN(16, 2);
   else if (P.L.queue_scan == 1) RUN(16, 1);
-  else if (c->num_nodes <= 16) RUN(16, 0);
+  else if (P.L.queue_scan == 3) {
+    if (c->num_nodes <= 16) RUN(16, 3);
+    else if (c->num_nodes <= 32) RUN(32, 3);
+    else RUN(64, 3);
+  } else if (c->num_nodes <= 16) RUN(16, 0);
   else if (c->num_nodes <= 32) RUN(32, 0);
   else RUN(64, 0);
 #undef RUN

@@ -67,7 +67,9 @@ CASES = [
     (31, 32, 5, 1500, {"delta": 5, "gamma": 1.5, "lambda_": 0.25, "queue_cap": 4096, "payload_cap": 1024}),
     (41, 16, 4, 4000, {"target_commit_interval": 300, "delta": 400}),
     (61, 64, 4, 1000, {"queue_cap": 128}),   # 64-bit-key scan queue in HBM (QMODE 1)
-    (62, 40, 6, 1000, {}),                   # binary heap (QMODE 0) at small N
+    (62, 40, 6, 1000, {}),                   # calendar queue (QMODE 3)
+    (63, 8, 6, 4200, {}),                    # binary heap (QMODE 0): horizon beyond the calendar's range
+    (64, 12, 9, 700, {"delay_kind": 1, "delay_lo": 0, "delay_hi": 3, "round_cap": 256}),  # calendar queue with zero delays
 ]
 
 

@@ -22,7 +22,9 @@ CASES = [
     (31, 16, 5, 1500, {"delta": 5, "gamma": 1.5, "lambda_": 0.25, "queue_cap": 4096, "payload_cap": 1024}),   # tight pacemaker -> many timeouts, query-all
     (41, 8, 4, 4000, {"target_commit_interval": 300, "delta": 400}),  # commit tracker query-all path
     (61, 16, 4, 1000, {"queue_cap": 128}),   # forces the 64-bit-key scan queue in HBM (QMODE 1)
-    (62, 8, 6, 1000, {}),                    # heap (QMODE 0) at small N
+    (62, 8, 6, 1000, {}),                    # calendar queue (QMODE 3)
+    (63, 4, 6, 4200, {}),                    # binary heap (QMODE 0): horizon beyond the calendar's range
+    (64, 6, 9, 700, {"delay_kind": 1, "delay_lo": 0, "delay_hi": 3, "round_cap": 256}),  # calendar queue, zero delays (same-slot pushes)
 ]
 
 
@@ -65,7 +67,8 @@ def test_fast_paths_are_selected_for_the_benchmark_config(hostcore):
     assert info["delay_kmax"] > 100 and info["queue_scan"] == 2 and info["round_cap"] == 128
     assert hostcore.setup_info(4, 20000)["queue_scan"] == 1                         # long horizon: 64-bit keys in HBM
     assert hostcore.setup_info(4, 1000, delay_variance=0.0)["delay_kmax"] == 0      # constant delay: host-evaluated
-    assert hostcore.setup_info(16, 1000)["queue_scan"] == 0                         # big committees: heap
+    assert hostcore.setup_info(16, 1000)["queue_scan"] == 3                         # big committees: calendar queue
+    assert hostcore.setup_info(16, 5000)["queue_scan"] == 0                         # long horizons: binary heap
 
 
 def test_delay_table_equals_libm_exp_path(oracle, hostcore):
