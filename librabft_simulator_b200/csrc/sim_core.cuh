@@ -31,6 +31,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "sim_params.h"
 
 #if defined(__CUDACC__)
@@ -80,6 +82,13 @@ LBFT_HD uint32_t ctz64(uint64_t x) {
   return (uint32_t)(__ffsll((long long)x) - 1);
 #else
   return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+LBFT_HD uint32_t ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)(__ffs((int)x) - 1);
+#else
+  return (uint32_t)__builtin_ctz(x);
 #endif
 }
 LBFT_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
@@ -349,14 +358,15 @@ struct Core {
   // memory helpers
   // ------------------------------------------------------------------------------------------
   LBFT_HD uint32_t nbase(uint32_t n) const { return L.node_base + n * L.node_words; }
-  LBFT_HD static uint64_t ld_mask(const uint32_t* p) {
+  using mask_t = typename std::conditional<(NMAX > 32), uint64_t, uint32_t>::type;  // one bit per author
+  LBFT_HD static mask_t ld_mask(const uint32_t* p) {
     uint64_t v = p[0];
     if (NMAX > 32) v |= (uint64_t)p[S] << 32;
-    return v;
+    return (mask_t)v;
   }
-  LBFT_HD static void st_mask(uint32_t* p, uint64_t v) {
+  LBFT_HD static void st_mask(uint32_t* p, mask_t v) {
     p[0] = (uint32_t)v;
-    if (NMAX > 32) p[S] = (uint32_t)(v >> 32);
+    if (NMAX > 32) p[S] = (uint32_t)((uint64_t)v >> 32);
   }
   LBFT_HD static uint32_t ld_u16(const uint32_t* p, uint32_t i) { return (p[(i >> 1) * S] >> (16 * (i & 1))) & 0xffffu; }
   LBFT_HD static void st_u16(uint32_t* p, uint32_t i, uint32_t v) {
@@ -385,7 +395,7 @@ struct Core {
   // only the 32-round word around the node's current round is cached (cw); other words go to memory.
   struct NodeRegs {
     uint32_t f[F_NSCALAR];
-    uint64_t vmask, tmask, tcmask;  // current_votes / current_timeouts / highest TC author sets
+    mask_t vmask, tmask, tcmask;  // current_votes / current_timeouts / highest TC author sets
     uint32_t cw;                    // index of the cached bitset word
     uint32_t chb, chq, cpd;         // cached words: block known / QC known / state pending
     uint32_t dirty;                 // bit0 chb, bit1 chq, bit2 cpd modified
@@ -630,8 +640,18 @@ struct Core {
   }
 
   // notification payload pool (DataSyncNotification snapshots, shared by all receivers of one send)
+  // Slot allocator.  payload_cap <= 32: a free-slot bitmask in a register (pay_free = mask of FREE slots, no memory
+  // traffic); otherwise a free list threaded through word [2] of the free slots plus a bump pointer.
+  // pay_next is the high-water mark of slots ever used in both cases (reported as max_payloads).
   LBFT_HD uint32_t pay_alloc() {
     uint32_t s;
+    if (L.payload_cap <= 32) {
+      if (pay_free == 0) { status |= ST_PAYLOAD_OVERFLOW; return PAY_NONE; }
+      s = ctz32(pay_free);
+      pay_free &= pay_free - 1;
+      if (s >= pay_next) pay_next = s + 1;
+      return s;
+    }
     if (pay_free != PAY_NONE) {
       s = pay_free;
       pay_free = m.ld(L.pay_base + s * L.pay_words + 2) & 0xffffu;
@@ -643,8 +663,9 @@ struct Core {
     }
     return s;
   }
-  LBFT_HD void pay_release(uint32_t s) {  // link into the free list through word [2]
-    m.st(L.pay_base + s * L.pay_words + 2, pay_free);
+  LBFT_HD void pay_release(uint32_t s) {
+    if (L.payload_cap <= 32) { pay_free |= 1u << s; return; }
+    m.st(L.pay_base + s * L.pay_words + 2, pay_free);  // link into the free list through word [2]
     pay_free = s;
   }
   LBFT_HD void pay_unref(uint32_t slot, uint32_t w2) {
@@ -688,7 +709,7 @@ struct Core {
     if (r != d.f[F_CUR]) return;
     if (!has_blk(d, r)) return;
     if ((d.vmask >> author) & 1) return;
-    d.vmask |= 1ULL << author;
+    d.vmask |= (mask_t)1 << author;
     if (election(d) == 0) {
       d.f[F_BALLOT] += P.weights[author];
       if (d.f[F_BALLOT] >= P.quorum) set_election(d, 1);
@@ -718,7 +739,7 @@ struct Core {
     if (hcbr > d.f[F_HQC]) return;
     if (round != d.f[F_CUR]) return;
     if ((d.tmask >> author) & 1) return;
-    d.tmask |= 1ULL << author;
+    d.tmask |= (mask_t)1 << author;
     st_u16(d.nb + L.n_thcbr * S, author, hcbr);
     d.f[F_TOW] += P.weights[author];
     if (d.f[F_TOW] >= P.quorum) {
@@ -877,7 +898,7 @@ struct Core {
     pb[0] = d.f[F_HCC] | (d.f[F_HQC] << 16);
     pb[1 * S] = d.f[F_CUR] | ((has_tc ? d.f[F_TC_ROUND] : 0u) << 16);
     pb[2 * S] = refs | ((vote | (prop << 1)) << 16);
-    st_mask(pb + L.p_tcmask * S, has_tc ? d.tcmask : 0);
+    st_mask(pb + L.p_tcmask * S, has_tc ? d.tcmask : (mask_t)0);
     st_mask(pb + L.p_curmask * S, d.tmask);
     // receivers read a timeout's highest_certified_block_round only for authors in the masks
     if (has_tc)
@@ -889,7 +910,7 @@ struct Core {
   LBFT_HD bool handle_notification(NodeRegs& d, uint32_t slot, uint32_t sender) {
     uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
     uint32_t w0 = pb[0], w1 = pb[1 * S], w2 = pb[2 * S];
-    uint64_t tcm = ld_mask(pb + L.p_tcmask * S), curm = ld_mask(pb + L.p_curmask * S);
+    mask_t tcm = ld_mask(pb + L.p_tcmask * S), curm = ld_mask(pb + L.p_curmask * S);
     uint32_t hcc = w0 & 0xffffu, hqc = w0 >> 16, cur_s = w1 & 0xffffu, tc_round = w1 >> 16;
     bool vote = (w2 >> 16) & 1, prop = (w2 >> 17) & 1;
     bool should_sync = false;
@@ -909,11 +930,11 @@ struct Core {
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {
       uint32_t round = which ? cur_s : tc_round;
-      uint64_t mask = which ? curm : tcm;
+      mask_t mask = which ? curm : tcm;
       if (round != 0 && round == d.f[F_CUR]) {
         const uint32_t* hp = pb + (which ? L.p_curhcbr : L.p_tchcbr) * S;
         while (mask) {
-          uint32_t a = ctz64(mask);
+          uint32_t a = NMAX > 32 ? ctz64((uint64_t)mask) : ctz32((uint32_t)mask);
           mask &= mask - 1;
           insert_timeout(d, round, ld_u16(hp, a), a);
         }
@@ -964,7 +985,8 @@ struct Core {
     const uint32_t N = L.num_nodes;
     seed_rng(seed, s0, s1, s2, s3);
     draws = 0; stamp = 0; qsize = 0; status = 0; clock = 0;
-    pay_free = PAY_NONE; pay_next = 0;
+    pay_free = L.payload_cap <= 32 ? (L.payload_cap == 32 ? 0xffffffffu : ((1u << L.payload_cap) - 1)) : PAY_NONE;
+    pay_next = 0;
     proc0 = proc1 = proc2 = proc3 = cancelled = max_queue = sched_notify = dedup = 0;
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
