@@ -74,3 +74,18 @@ def test_two_handles_are_independent():
     assert r1.commit_counts.shape == (32, 4) and r2.commit_counts.shape == (32, 7)
     assert r1.commit_counts.min() > 10
     s1.close(); s2.close()
+
+
+def test_commit_log_truncation_and_bounds():
+    from librabft_simulator_b200 import _lib
+    sim = make(np.arange(52, 84, dtype=np.uint64), nodes=3).create(1000)
+    res = sim.run()
+    n = ctypes.c_size_t()
+    buf = (_lib.LbftCommit * 5)()
+    assert sim._lib.lbft_commit_log(sim._handle, 0, 0, buf, 5, ctypes.byref(n)) == 0
+    assert n.value == 27                      # seed 52 / 3 nodes: the reference golden (simulated_run.rs:53)
+    full = sim.commit_log(0, 0)
+    assert [(buf[i].proposer, buf[i].index, buf[i].time) for i in range(5)] == full[:5]
+    assert sim._lib.lbft_commit_log(sim._handle, 32, 0, buf, 5, ctypes.byref(n)) == -1   # instance out of range
+    assert sim._lib.lbft_commit_log(sim._handle, 0, 3, buf, 5, ctypes.byref(n)) == -1    # node out of range
+    sim.close()

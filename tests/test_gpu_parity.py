@@ -147,3 +147,13 @@ def test_gpu_extensions_match_oracle(oracle, name, seed0, count, nodes, max_cloc
     assert_same(o, g, name)
     assert sim.commit_log(count - 1, nodes - 2 if nodes > 1 else 0) == oracle.commit_log(
         seeds, nodes, count - 1, nodes - 2 if nodes > 1 else 0, max_clock, **extra)
+
+
+@pytest.mark.parametrize("nodes,count,seed0", [(3, 4096, 10_000), (4, 8192, 20_000), (5, 2048, 30_000), (7, 1024, 40_000)])
+def test_wide_seed_sweep_matches_oracle(oracle, nodes, count, seed0):
+    # every instance of a few thousand seeds, compared in full (the oracle needs ~1 ms per instance and core)
+    seeds = np.arange(seed0, seed0 + count, dtype=np.uint64)
+    o = oracle.run(seeds, nodes, 1000)
+    sim, g = gpu_run(seeds, nodes, 1000)
+    assert (o.status == 1).all() and ((g.status & ~np.uint32(64)) == 1).all()
+    assert_same(o, g, "sweep N=%d" % nodes)
