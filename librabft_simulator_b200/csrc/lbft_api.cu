@@ -33,10 +33,7 @@ static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter 
 // Block = 1 warp so that the 2048 tiles of a 65 536-instance batch spread evenly over 148 SMs.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 32;
-constexpr uint32_t kThrSmem = 160;   // doubles: delay thresholds that fit in shared memory
-constexpr uint32_t kRoundSmem = 132;  // rounds (incl. round_cap itself) whose leader/duration/period fit in shared memory
-constexpr uint32_t kNodeSmem = 64;
-// static shared memory: 2*257*8 (ziggurat) + 160*8 + 2*132*4 + 64*4 + 132 = 6 840 B
+constexpr uint32_t kThrSmem = 256;  // doubles
 
 // Launch shapes.  QMODE 0/1: one-warp blocks, 14 resident per SM (2 048 tiles of a 65 536-instance batch over 148
 // SMs; <= 144 registers/thread keeps every tile resident).  QMODE 2: two-warp blocks, 7 per SM, so that the
@@ -56,10 +53,6 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
   __shared__ double s_zx[257];
   __shared__ double s_zf[257];
   __shared__ double s_thr[kThrSmem];  // delay thresholds (same scattered access pattern), when they fit
-  __shared__ int32_t s_duration[kRoundSmem];
-  __shared__ int32_t s_period[kRoundSmem];
-  __shared__ uint32_t s_weights[kNodeSmem];
-  __shared__ uint8_t s_leader[kRoundSmem];
   extern __shared__ uint32_t s_queue[];  // QMODE 2: per warp [queue_cap][32] u32 keys, then [queue_cap][32] u16 payload words
   for (int i = threadIdx.x; i < 257; i += blockDim.x) {
     s_zx[i] = P.zig_x[i];
@@ -68,14 +61,6 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
   const bool thr_fits = P.delay_kmax != 0 && P.delay_kmax + 2 <= kThrSmem;
   if (thr_fits)
     for (uint32_t i = threadIdx.x; i < P.delay_kmax + 2; i += blockDim.x) s_thr[i] = P.delay_thr[i];
-  const bool rounds_fit = P.L.round_cap + 1 <= kRoundSmem;
-  if (rounds_fit)
-    for (uint32_t i = threadIdx.x; i <= P.L.round_cap; i += blockDim.x) {
-      s_leader[i] = P.leader[i];
-      s_duration[i] = P.duration[i];
-      s_period[i] = P.period[i];
-    }
-  for (uint32_t i = threadIdx.x; i < P.L.num_nodes; i += blockDim.x) s_weights[i] = P.weights[i];
   __syncthreads();
   const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
   if (inst >= P.num_instances) return;
@@ -90,8 +75,6 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
   Core<TileMem<32>, NMAX, QMODE> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
-  if (rounds_fit) core.set_fast_round_tables(s_leader, s_duration, s_period);
-  core.set_fast_weights(s_weights);
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);

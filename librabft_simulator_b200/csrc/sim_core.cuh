@@ -265,13 +265,6 @@ struct Core {
   const double* zx;
   const double* zf;
   const double* thr;  // delay thresholds (shared-memory copy on the device when it fits)
-  // small launch-invariant tables: optional fast copies (shared memory on the device).  The fast and the global
-  // pointers are kept apart and selected by a flag, so that no pointer variable ever mixes address spaces.
-  const uint8_t* f_leader = nullptr;
-  const int32_t* f_duration = nullptr;
-  const int32_t* f_period = nullptr;
-  const uint32_t* f_weights = nullptr;
-  bool fast_rounds = false, fast_weights = false;
   uint32_t* sk;       // QMODE 2: this lane's key column,  sk[j * 32] = time:14 | 3-kind:2 | stamp:16
   uint16_t* sd;       // QMODE 2: this lane's data column, sd[j * 32] = slot:8 | sender:4 | receiver:4
   // ---- per-instance registers ----
@@ -285,20 +278,11 @@ struct Core {
   uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify, dedup;
   uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
   uint32_t cal_t, cal_free, cal_next;  // QMODE 3: current bucket time, pool free list head, pool bump pointer
-  uint32_t inv_seen;            // non-zero: a per-round "created once" bit was already set (checked lazily)
   uint32_t cc0, cc1, cc2, cc3;  // chain cache: (round << 16) | previous QC round
 
   LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_, uint32_t* sk_ = nullptr,
                uint16_t* sd_ = nullptr)
       : P(p), L(p.L), m(mem), zx(zx_), zf(zf_), thr(thr_), sk(sk_), sd(sd_) {}
-  LBFT_HD void set_fast_round_tables(const uint8_t* leader, const int32_t* duration, const int32_t* period) {
-    f_leader = leader; f_duration = duration; f_period = period; fast_rounds = true;
-  }
-  LBFT_HD void set_fast_weights(const uint32_t* weights) { f_weights = weights; fast_weights = true; }
-  LBFT_HD uint32_t leader_at(uint32_t r) const { return fast_rounds ? f_leader[r] : P.leader[r]; }
-  LBFT_HD int32_t duration_at(uint32_t n) const { return fast_rounds ? f_duration[n] : P.duration[n]; }
-  LBFT_HD int32_t period_at(uint32_t n) const { return fast_rounds ? f_period[n] : P.period[n]; }
-  LBFT_HD uint32_t weight_of(uint32_t a) const { return fast_weights ? f_weights[a] : P.weights[a]; }
 
   // ------------------------------------------------------------------------------------------
   // RNG (rand_xoshiro 0.6.0 / rand 0.8.3 / rand_distr 0.4.0)
@@ -390,19 +374,8 @@ struct Core {
     uint32_t sh = 16 * (i & 1);
     p[(i >> 1) * S] = (x & ~(0xffffu << sh)) | (v << sh);
   }
-  // Set bit r of a per-instance bitset and remember whether it was already set (an App. C.1 violation).  The old
-  // value is only inspected at the end of the iteration, so the read-modify-write never stalls the protocol code.
-  LBFT_HD void mbit_set_checked(uint32_t w, uint32_t r) {
-    uint32_t* p = m.at(w + (r >> 5));
-    uint32_t bit = 1u << (r & 31);
-#if defined(__CUDA_ARCH__)
-    uint32_t old = atomicOr(p, bit);
-#else
-    uint32_t old = *p;
-    *p = old | bit;
-#endif
-    inv_seen |= old & bit;
-  }
+  LBFT_HD bool mbit_test(uint32_t w, uint32_t r) const { return (m.ld(w + (r >> 5)) >> (r & 31)) & 1u; }
+  LBFT_HD void mbit_set(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) | (1u << (r & 31))); }
   // previous-QC round of block r.  The last few proposals of the instance are kept in a 4-entry direct-mapped
   // register cache (written through at propose time), which serves nearly every lookup without a dependent load.
   LBFT_HD uint32_t chain_prev(uint32_t r) const {
@@ -738,7 +711,7 @@ struct Core {
     if ((d.vmask >> author) & 1) return;
     d.vmask |= (mask_t)1 << author;
     if (election(d) == 0) {
-      d.f[F_BALLOT] += weight_of(author);
+      d.f[F_BALLOT] += P.weights[author];
       if (d.f[F_BALLOT] >= P.quorum) set_election(d, 1);
     }
   }
@@ -768,7 +741,7 @@ struct Core {
     if ((d.tmask >> author) & 1) return;
     d.tmask |= (mask_t)1 << author;
     st_u16(d.nb + L.n_thcbr * S, author, hcbr);
-    d.f[F_TOW] += weight_of(author);
+    d.f[F_TOW] += P.weights[author];
     if (d.f[F_TOW] >= P.quorum) {
       d.tcmask = d.tmask;
       for (uint32_t i = 0; i < L.hcbr_words; i++) d.nb[(L.n_tchcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
@@ -783,7 +756,8 @@ struct Core {
     uint32_t idx = d.f[F_NEXT_CMD]++;
     uint32_t r = d.f[F_CUR];
     if (idx > 0xffffu) status |= ST_ROUND_OVERFLOW;
-    mbit_set_checked(L.created_base, r);  // App. C.1: a second block in a round raises LBFT_ST_INVARIANT
+    if (mbit_test(L.created_base, r)) status |= ST_INVARIANT;  // App. C.1: second block in a round
+    mbit_set(L.created_base, r);
     m.st(L.chain_base + 2 * r, prev_round | (idx << 16));
     m.st(L.chain_base + 2 * r + 1, (uint32_t)clk);
     chain_cache_put(r, prev_round);
@@ -832,12 +806,12 @@ struct Core {
     if (active > d.f[F_PMR]) {
       d.f[F_PMR] = active;
       d.f[F_PM_START] = (uint32_t)clk;
-      uint32_t ld = leader_at(active);
+      uint32_t ld = P.leader[active];
       d.f[F_FLAGS] = (d.f[F_FLAGS] & ~(0xffu << FL_LEADER_SHIFT)) | (ld << FL_LEADER_SHIFT);
       uint32_t base = d.f[F_HCR] > 0 ? d.f[F_HCR] + 2 : 0;  // duration(), :111-124
       if (!(active > base)) { status |= ST_INVARIANT; base = active - 1; }
-      d.f[F_PM_DUR] = (uint32_t)duration_at(active - base);
-      d.f[F_PM_PERIOD] = (uint32_t)period_at(active - base);
+      d.f[F_PM_DUR] = (uint32_t)P.duration[active - base];
+      d.f[F_PM_PERIOD] = (uint32_t)P.period[active - base];
       if (ld != n) a.send_to = (int32_t)ld;
     }
     const uint32_t leader = leader_of(d);
@@ -887,9 +861,10 @@ struct Core {
     // ---- check_for_new_quorum_certificate (record_store.rs:702-738) and QC broadcast, node.rs:277-283
     if (election(d) == 1) {
       uint32_t r = d.f[F_CUR];
-      if (leader_at(r) == n) {
+      if (P.leader[r] == n) {
         set_election(d, 2);
-        mbit_set_checked(L.qcmade_base, r);  // App. C.1: a second QC in a round raises LBFT_ST_INVARIANT
+        if (mbit_test(L.qcmade_base, r)) status |= ST_INVARIANT;  // App. C.1: second QC in a round
+        mbit_set(L.qcmade_base, r);
         insert_qc(d, r);
         a.broadcast = true;
         a.next = clk;
@@ -915,20 +890,7 @@ struct Core {
   // ------------------------------------------------------------------------------------------
   // DataSyncNode::create_notification (data_sync.rs:82-111) into a payload slot
   // ------------------------------------------------------------------------------------------
-  // hcbr snapshot words fetched before the send loop so that their latency hides behind the delay sampling
-  struct HcbrRegs {
-    uint32_t tc[2], cur[2];
-  };
-  LBFT_HD void prefetch_hcbr(const NodeRegs& d, HcbrRegs& h) const {
-    if (L.hcbr_words > 2) return;
-    const bool has_tc = d.f[F_FLAGS] & FL_HAS_TC;
-#pragma unroll
-    for (uint32_t i = 0; i < 2; i++) {
-      h.tc[i] = (has_tc && i < L.hcbr_words) ? d.nb[(L.n_tchcbr + i) * S] : 0u;
-      h.cur[i] = (d.tmask && i < L.hcbr_words) ? d.nb[(L.n_thcbr + i) * S] : 0u;
-    }
-  }
-  LBFT_HD void write_notification(uint32_t n, const NodeRegs& d, uint32_t slot, uint32_t refs, const HcbrRegs& h) {
+  LBFT_HD void write_notification(uint32_t n, const NodeRegs& d, uint32_t slot, uint32_t refs) {
     uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
     bool has_tc = d.f[F_FLAGS] & FL_HAS_TC;
     uint32_t vote = (uint32_t)((d.vmask >> n) & 1);  // current_vote(author), record_store.rs:762-764
@@ -939,36 +901,16 @@ struct Core {
     st_mask(pb + L.p_tcmask * S, has_tc ? d.tcmask : (mask_t)0);
     st_mask(pb + L.p_curmask * S, d.tmask);
     // receivers read a timeout's highest_certified_block_round only for authors in the masks
-    if (L.hcbr_words <= 2) {
-#pragma unroll
-      for (uint32_t i = 0; i < 2; i++) {
-        if (has_tc && i < L.hcbr_words) pb[(L.p_tchcbr + i) * S] = h.tc[i];
-        if (d.tmask && i < L.hcbr_words) pb[(L.p_curhcbr + i) * S] = h.cur[i];
-      }
-    } else {
-      if (has_tc)
-        for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_tchcbr + i) * S] = d.nb[(L.n_tchcbr + i) * S];
-      if (d.tmask)
-        for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_curhcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
-    }
-  }
-  // The fixed part of a notification, fetched right after the pop (together with the node's state) so that the two
-  // batches of loads overlap.
-  struct NotifRegs {
-    uint32_t w0, w1, w2;
-    mask_t tcm, curm;
-  };
-  LBFT_HD void load_notification(uint32_t slot, NotifRegs& q) const {
-    const uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
-    q.w0 = pb[0]; q.w1 = pb[1 * S]; q.w2 = pb[2 * S];
-    q.tcm = ld_mask(pb + L.p_tcmask * S);
-    q.curm = ld_mask(pb + L.p_curmask * S);
+    if (has_tc)
+      for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_tchcbr + i) * S] = d.nb[(L.n_tchcbr + i) * S];
+    if (d.tmask)
+      for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_curhcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
   }
   // DataSyncNode::handle_notification (data_sync.rs:113-177).  Returns should_sync.
-  LBFT_HD bool handle_notification(NodeRegs& d, uint32_t slot, uint32_t sender, const NotifRegs& q) {
+  LBFT_HD bool handle_notification(NodeRegs& d, uint32_t slot, uint32_t sender) {
     uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
-    const uint32_t w0 = q.w0, w1 = q.w1, w2 = q.w2;
-    const mask_t tcm = q.tcm, curm = q.curm;
+    uint32_t w0 = pb[0], w1 = pb[1 * S], w2 = pb[2 * S];
+    mask_t tcm = ld_mask(pb + L.p_tcmask * S), curm = ld_mask(pb + L.p_curmask * S);
     uint32_t hcc = w0 & 0xffffu, hqc = w0 >> 16, cur_s = w1 & 0xffffu, tc_round = w1 >> 16;
     bool vote = (w2 >> 16) & 1, prop = (w2 >> 17) & 1;
     bool should_sync = false;
@@ -1049,7 +991,6 @@ struct Core {
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
     cal_t = 0; cal_free = PAY_NONE; cal_next = 0;
-    inv_seen = 0;
     if (QMODE == 3)
       for (uint32_t w = 0; w < (L.cal_times + 7) / 8; w++) m.st(L.cal_kmask + w, 0);
     for (uint32_t w = 0; w < N * L.node_words; w++) m.st(L.node_base + w, 0);
@@ -1119,15 +1060,13 @@ struct Core {
       a.query_all = false;
       bool should_sync = false;
       const bool is_request = kind == EV_REQUEST;  // answered by `receiver` itself (simulator.rs:446): no state change
-      NotifRegs nq;
-      if (kind == EV_NOTIFY) load_notification(slot, nq);
       if (!is_request) {
         load_node(receiver, d);
         if (kind == EV_TIMER && clock <= (int32_t)d.f[F_IGNORE]) {
           cancelled++;
           continue;
         }
-        if (kind == EV_NOTIFY) should_sync = handle_notification(d, slot, sender, nq);
+        if (kind == EV_NOTIFY) should_sync = handle_notification(d, slot, sender);
         a = update_node(receiver, d, clock - (int32_t)d.f[F_STARTUP]);
         // next UpdateTimerEvent, simulator.rs:311-324
         int64_t from_node = a.next == NODE_TIME_NEVER ? (int64_t)0x7fffffff : (int64_t)a.next + (int32_t)d.f[F_STARTUP];
@@ -1172,11 +1111,9 @@ struct Core {
         }
         for (uint32_t i = list.len; i-- > 1;) list.swap(i, gen_range_u32(i + 1));  // SliceRandom::shuffle
         if (list.len == 0) continue;
-        HcbrRegs hc;
         if (to_other) {
           pslot = pay_alloc();
           sched_notify += list.len;
-          prefetch_hcbr(d, hc);
         }
         uint32_t queued = 0;
 #pragma unroll 1
@@ -1186,13 +1123,12 @@ struct Core {
           if (schedule_network_event(ev_kind, ev_recv, ev_send, pslot)) queued++;
         }
         if (to_other && pslot != PAY_NONE) {
-          if (queued) write_notification(receiver, d, pslot, queued, hc);
+          if (queued) write_notification(receiver, d, pslot, queued);
           else pay_release(pslot);
         }
       }
       if (!is_request) store_node(d);
     }
-    if (inv_seen) status |= ST_INVARIANT;
     if (!(status & ST_FATAL)) status |= ST_DONE;
   }
 
