@@ -145,9 +145,11 @@ struct HostSetup {
     uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 4 ? 32u : (N <= 8 ? 64u : pow2_ceil(8 * N)));
     if (pcap > 0xfff0u) return fail("payload_cap must be < 65520");
     // shortest horizons: 32-bit keys (time:14 | kind:2 | stamp:16) + 16-bit payload words, queue in shared memory
-    // (16-bit stamps: ~0.14 N^2 events are created per simulated ms at the reference delay; stay well inside 65 536)
-    if (qscan && c.max_clock < (1 << 14) - 64 && qcap <= 64 && pcap <= 255 &&
-        0.14 * N * N * (double)c.max_clock < 32768.0)
+    // (16-bit stamps: ~0.14 N^2 events are created per simulated ms at the reference's 10 ms mean delay, and
+    // proportionally more with shorter delays; stay well inside 65 536 — an overflow would be flagged, not silent)
+    const double mean_delay = c.delay_kind == LBFT_DELAY_UNIFORM ? 0.5 * (double)(c.delay_lo + c.delay_hi) : c.delay_mean;
+    const double events_per_ms = 0.14 * N * N * (10.0 / (mean_delay < 1.0 ? 1.0 : mean_delay));
+    if (qscan && c.max_clock < (1 << 14) - 64 && qcap <= 64 && pcap <= 255 && events_per_ms * (double)c.max_clock < 32768.0)
       qscan = 2;
     // everything else with a moderate horizon: calendar queue (O(1) push/pop, exact: FIFO order inside a (time, kind)
     // list is creation-stamp order); the binary heap remains for long horizons
