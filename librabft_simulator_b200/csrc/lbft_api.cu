@@ -29,11 +29,10 @@ static_assert(LBFT_SAME(ST_DONE, LBFT_ST_DONE) && LBFT_SAME(ST_ROUND_OVERFLOW, L
 static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter layout");
 
 // ---------------------------------------------------------------------------------------------
-// Kernel: one thread per simulator instance, one warp per 32-instance tile.
-// Block = 1 warp so that the 2048 tiles of a 65 536-instance batch spread evenly over 148 SMs.
+// Kernel: one thread per simulator instance, one warp per 32-instance tile; init -> event loop -> read-out in a
+// single launch.  Small blocks so that the 2 048 tiles of a 65 536-instance batch spread evenly over 148 SMs.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBlockThreads = 32;
-constexpr uint32_t kThrSmem = 256;  // doubles
+constexpr uint32_t kThrSmem = 256;  // doubles: delay thresholds held in shared memory when they fit
 
 // Launch shapes.  QMODE 0/1: one-warp blocks, 14 resident per SM (2 048 tiles of a 65 536-instance batch over 148
 // SMs; <= 144 registers/thread keeps every tile resident).  QMODE 2: two-warp blocks, 7 per SM, so that the
