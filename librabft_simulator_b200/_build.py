@@ -10,7 +10,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "librabft_simulator_b200", "csrc")
-LIB_PATH = os.path.join(CSRC, "liblbft_b200.so")
+LIB_PATH = os.environ.get("LBFT_LIB_PATH") or os.path.join(CSRC, "liblbft_b200.so")
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_PATH = os.path.join(ORACLE_DIR, "liblbft_oracle.so")
 HOSTCORE_DIR = os.path.join(ROOT, "tests", "hostcore")
@@ -66,7 +66,7 @@ def build_hostcore(force=False):
         os.path.join(CSRC, f) for f in ("sim_core.cuh", "sim_params.h", "host_setup.hpp")]
     if not force and _newer(HOSTCORE_PATH, srcs):
         return HOSTCORE_PATH
-    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas", "-DLBFT_CHECK_C1",
           "-o", HOSTCORE_PATH, "hostcore.cpp"], HOSTCORE_DIR)
     return HOSTCORE_PATH
 
