@@ -170,6 +170,7 @@ struct HostSetup {
       duration[n] = (int32_t)(dur > CL ? CL : (dur < -CL ? -CL : dur));
       period[n] = (int32_t)(per > CL ? CL : (per < -CL ? -CL : per));
     }
+    for (uint32_t i = 0; i < 64; i++) p.c_weights[i] = i < N ? weights[i] : 0;
     build_ziggurat();
     build_delay_table();
     return true;

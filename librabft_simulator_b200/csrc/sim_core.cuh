@@ -711,7 +711,7 @@ struct Core {
     if ((d.vmask >> author) & 1) return;
     d.vmask |= (mask_t)1 << author;
     if (election(d) == 0) {
-      d.f[F_BALLOT] += P.weights[author];
+      d.f[F_BALLOT] += P.c_weights[author];
       if (d.f[F_BALLOT] >= P.quorum) set_election(d, 1);
     }
   }
@@ -741,7 +741,7 @@ struct Core {
     if ((d.tmask >> author) & 1) return;
     d.tmask |= (mask_t)1 << author;
     st_u16(d.nb + L.n_thcbr * S, author, hcbr);
-    d.f[F_TOW] += P.weights[author];
+    d.f[F_TOW] += P.c_weights[author];
     if (d.f[F_TOW] >= P.quorum) {
       d.tcmask = d.tmask;
       for (uint32_t i = 0; i < L.hcbr_words; i++) d.nb[(L.n_tchcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
