@@ -196,10 +196,30 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries print on stdout (e.g. the NCCL version banner) to stderr, so that the ONE JSON line
+    the driver parses is the only thing on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -338,7 +358,7 @@ def main():
         if not args.no_cpu_baseline:
             base, cres, sample = cpu_baseline(per_gpu)
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
