@@ -44,7 +44,7 @@ struct LaunchShape {
   static constexpr int kBlocksPerSm = QMODE == 2 ? 7 : 14;
 };
 
-template <int NMAX, int QMODE>
+template <int NMAX, int QMODE, bool FIXED = false>
 __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<32>, NMAX, QMODE> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  Core<TileMem<32>, NMAX, QMODE, FIXED> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
@@ -290,7 +290,12 @@ int lbft_run_device(lbft_sim* s) {
     const size_t dyn = QM == 2 ? (size_t)(T / 32) * s->P.L.queue_cap * (32 * 4 + 32 * 2) : 0;                      \
     lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, s->stream>>>(s->P);                                        \
   } while (0)
-  if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);
+  // the default four-author layout has a kernel instantiation with compile-time field offsets
+  constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
+  if (s->P.L.queue_scan == 2 && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
+    constexpr int T = LaunchShape<2>::kThreads;
+    lbft_event_loop_kernel<16, 2, true><<<(s->I + T - 1) / T, T, (size_t)(T / 32) * 64 * (32 * 4 + 32 * 2), s->stream>>>(s->P);
+  } else if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);
   else if (s->P.L.queue_scan == 1) LBFT_LAUNCH(16, 1);
   else if (s->P.L.queue_scan == 3) {
     if (s->N <= 16) LBFT_LAUNCH(16, 3);

@@ -256,11 +256,13 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 
 // QMODE: 0 binary heap (3-word entries, HBM) | 1 scan queue, 64-bit keys in HBM | 2 scan queue, 32-bit keys +
 // 16-bit payload words in shared memory (small committees, short horizons) | 3 calendar queue in HBM
-template <class Mem, int NMAX, int QMODE>
+// FIXED: the layout is the compile-time constant make_layout(4, 128, 64, 32, 0, 2) (BASELINE configs 1-3: four authors,
+// default capacities) instead of the launch parameter block: every field offset folds into an immediate.
+template <class Mem, int NMAX, int QMODE, bool FIXED = false>
 struct Core {
   static constexpr int S = Mem::STRIDE;
   const Params& P;
-  const Layout& L;
+  const Layout L;
   Mem m;
   const double* zx;
   const double* zf;
@@ -282,7 +284,7 @@ struct Core {
 
   LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_, uint32_t* sk_ = nullptr,
                uint16_t* sd_ = nullptr)
-      : P(p), L(p.L), m(mem), zx(zx_), zf(zf_), thr(thr_), sk(sk_), sd(sd_) {}
+      : P(p), L(FIXED ? make_layout(4, 128, 64, 32, 0, 2) : p.L), m(mem), zx(zx_), zf(zf_), thr(thr_), sk(sk_), sd(sd_) {}
 
   // ------------------------------------------------------------------------------------------
   // RNG (rand_xoshiro 0.6.0 / rand 0.8.3 / rand_distr 0.4.0)

@@ -72,7 +72,12 @@ struct Layout {
   uint32_t p_tcmask, p_curmask, p_tchcbr, p_curhcbr;
 };
 
-inline Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
+#if defined(__CUDACC__)
+#define LBFT_LAYOUT_FN __host__ __device__ constexpr
+#else
+#define LBFT_LAYOUT_FN constexpr
+#endif
+LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
                           uint32_t queue_scan, uint32_t max_clock = 0) {
   Layout L{};
   L.queue_scan = queue_scan;
