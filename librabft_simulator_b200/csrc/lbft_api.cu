@@ -292,7 +292,9 @@ int lbft_run_device(lbft_sim* s) {
   } while (0)
   // the default four-author layout has a kernel instantiation with compile-time field offsets
   constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
-  if (s->P.L.queue_scan == 2 && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
+  const bool plain_model = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0 &&
+                           s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
+  if (s->P.L.queue_scan == 2 && plain_model && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
     constexpr int T = LaunchShape<2>::kThreads;
     lbft_event_loop_kernel<16, 2, true><<<(s->I + T - 1) / T, T, (size_t)(T / 32) * 64 * (32 * 4 + 32 * 2), s->stream>>>(s->P);
   } else if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);

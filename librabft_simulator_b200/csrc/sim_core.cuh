@@ -257,7 +257,9 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // QMODE: 0 binary heap (3-word entries, HBM) | 1 scan queue, 64-bit keys in HBM | 2 scan queue, 32-bit keys +
 // 16-bit payload words in shared memory (small committees, short horizons) | 3 calendar queue in HBM
 // FIXED: the layout is the compile-time constant make_layout(4, 128, 64, 32, 0, 2) (BASELINE configs 1-3: four authors,
-// default capacities) instead of the launch parameter block: every field offset folds into an immediate.
+// default capacities) instead of the launch parameter block: every field offset folds into an immediate.  The host
+// only selects it for the reference's own model (LogNormal delay served by the threshold table, no silent nodes, no
+// partitions), so those extension branches are compiled out as well.
 template <class Mem, int NMAX, int QMODE, bool FIXED = false>
 struct Core {
   static constexpr int S = Mem::STRIDE;
@@ -337,10 +339,10 @@ struct Core {
   }
   // GlobalTime::add_delay (simulator.rs:110-118): returns the delay in ms.
   LBFT_HD int32_t sample_delay() {
-    if (P.delay_kind == 1u) return (int32_t)(P.uni_lo + gen_range_u64(P.uni_span));
+    if (!FIXED && P.delay_kind == 1u) return (int32_t)(P.uni_lo + gen_range_u64(P.uni_span));
     double z = standard_normal();
-    if (P.delay_const) return (int32_t)P.delay_const_value;  // sigma == 0: exp(mu) evaluated by the host libm
-    if (P.delay_kmax) {
+    if (!FIXED && P.delay_const) return (int32_t)P.delay_const_value;  // sigma == 0: exp(mu) evaluated by the host libm
+    if (FIXED || P.delay_kmax) {
       // (exp(mu + sigma*z) as i64) == number of thresholds <= z; the thresholds were bisected on the host
       // with the host libm, so this is exact.  Any starting guess works; the walk fixes it up.
       float g = expf((float)P.mu + (float)P.sigma * (float)z);
@@ -1077,7 +1079,7 @@ struct Core {
       proc2 += kind == EV_RESPONSE;
       proc3 += kind == EV_TIMER;
       // EXTENSION D.2: silent nodes handle nothing and answer no request
-      if (P.silent_mask) {
+      if (!FIXED && P.silent_mask) {
         bool drop = (P.silent_mask >> receiver) & 1;
         if (kind == EV_REQUEST && ((P.silent_mask >> sender) & 1)) drop = true;
         if (drop) {
