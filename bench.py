@@ -348,7 +348,7 @@ def main():
             "gpu_launches": args.steps * 2,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "lbft_event_loop_kernel<16,2>", "kernel_ms": k_ms,
+                         "kernel": "lbft_event_loop_kernel<16,2,true>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": bytes_launch,
                          "events_per_s": events_last / (k_ms * 1e-3)},
             "clocks": clocks,
