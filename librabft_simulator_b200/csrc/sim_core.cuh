@@ -1118,8 +1118,10 @@ struct Core {
       // run inside the notification pass (nothing of the same instance lies between them in the RNG stream).
       AuthorList<(NMAX <= 16 ? 16 : 64)> list;
       bool query_pending = a.query_all;
+      // (a lane only enters the passes it has something to do in: pass 0 when it owes a sync request, pass 2 when a
+      // query-all is still pending after pass 1)
 #pragma unroll 1
-      for (int phase = 0; phase < 3; phase++) {
+      for (int phase = should_sync ? 0 : 1; phase < 2 || (phase == 2 && query_pending); phase++) {
         uint32_t ev_kind = EV_REQUEST, pslot = PAY_NONE;
         bool to_other = false;  // notifications travel to `other`; requests/responses are addressed to the node itself
         list.clear();
