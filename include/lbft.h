@@ -64,6 +64,18 @@ typedef struct lbft_commit {
   int64_t time;
 } lbft_commit;
 
+/* One entry of DataWriter::nodes_round_switch (data_writer.rs:14, 34-50): at the pop of an event with
+ * scheduled time `time`, node `node` was seen with ActiveRound::active_round() == `round`, larger than
+ * at any earlier pop (simulator.rs:393-394: sampled after the max_clock test, before the clock max()). */
+typedef struct lbft_round_switch {
+  uint32_t node;
+  uint32_t round;
+  int64_t time;
+} lbft_round_switch;
+
+/* lbft_config.flags */
+#define LBFT_FLAG_ROUND_SWITCHES 1u /* record round switches = loop_until(.., Some(csv_path)) simulator.rs:380-381 */
+
 /* Per-instance event counters (simulator.rs:31 event_count; data_writer.rs message counter). */
 typedef struct lbft_instance_counters {
   uint32_t processed[4];      /* popped events by Event::kind(): 0 notify 1 request 2 response 3 timer */
@@ -116,7 +128,7 @@ typedef struct lbft_config {
   uint32_t round_cap;             /* rounds representable per instance                                 */
   uint32_t queue_cap;             /* pending events per instance                                       */
   uint32_t payload_cap;           /* in-flight notifications per instance                              */
-  uint32_t flags;                 /* reserved, must be 0                                               */
+  uint32_t flags;                 /* LBFT_FLAG_* bits; unknown bits are rejected                       */
   uint32_t reserved;
 } lbft_config;
 
@@ -147,6 +159,11 @@ int lbft_commit_counts(lbft_sim* sim, uint32_t* out);
 int lbft_last_states(lbft_sim* sim, uint64_t* out);
 /* committed_history() of one node; writes min(*n, cap) rows, *n = full length. */
 int lbft_commit_log(lbft_sim* sim, uint32_t instance, uint32_t node, lbft_commit* out, size_t cap, size_t* n);
+/* Round switches of one instance (needs LBFT_FLAG_ROUND_SWITCHES, else LBFT_ERR_STATE): node-major,
+ * rounds ascending within a node; writes min(*n, cap) rows, *n = full length.  Replaces the data behind
+ * DataWriter::write_to_file's round_switches.txt (data_writer.rs:61-86); number_of_messages.txt is
+ * processed[0] + processed[1] + processed[2] of lbft_counters. */
+int lbft_round_switches(lbft_sim* sim, uint32_t instance, lbft_round_switch* out, size_t cap, size_t* n);
 /* Per-instance counters and status flags: out[num_instances]. */
 int lbft_counters(lbft_sim* sim, lbft_instance_counters* out);
 int lbft_status(lbft_sim* sim, uint32_t* out);

@@ -28,6 +28,14 @@ class LbftCommit(ctypes.Structure):
     _fields_ = [("proposer", c_u32), ("index", c_u32), ("time", c_i64)]
 
 
+class LbftRoundSwitch(ctypes.Structure):
+    """include/lbft.h lbft_round_switch (data_writer.rs:14)"""
+    _fields_ = [("node", c_u32), ("round", c_u32), ("time", c_i64)]
+
+
+FLAG_ROUND_SWITCHES = 1  # LBFT_FLAG_ROUND_SWITCHES
+
+
 class LbftTiming(ctypes.Structure):
     _fields_ = [("init_ms", c_f64), ("sim_ms", c_f64), ("finalize_ms", c_f64), ("h2d_ms", c_f64), ("d2h_ms", c_f64),
                 ("h2d_bytes", c_u64), ("d2h_bytes", c_u64), ("kernel_launches", c_u32), ("reserved", c_u32)]
@@ -41,7 +49,7 @@ ST_ERROR_MASK = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST
 
 EXPORTS = [
     "lbft_create", "lbft_run", "lbft_upload", "lbft_run_device", "lbft_download", "lbft_commit_counts",
-    "lbft_last_states", "lbft_commit_log", "lbft_counters", "lbft_status", "lbft_timing_info",
+    "lbft_last_states", "lbft_commit_log", "lbft_round_switches", "lbft_counters", "lbft_status", "lbft_timing_info",
     "lbft_memory_info", "lbft_set_seeds", "lbft_device_buffer", "lbft_destroy", "lbft_last_error", "lbft_abi_version",
 ]
 
@@ -71,6 +79,7 @@ def load():
     for name in ("lbft_commit_counts", "lbft_last_states", "lbft_counters", "lbft_status"):
         getattr(lib, name).argtypes = [P, P]
     lib.lbft_commit_log.argtypes = [P, c_u32, c_u32, ctypes.POINTER(LbftCommit), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    lib.lbft_round_switches.argtypes = [P, c_u32, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.lbft_timing_info.argtypes = [P, ctypes.POINTER(LbftTiming)]
     lib.lbft_memory_info.argtypes = [P, ctypes.POINTER(c_u64), ctypes.POINTER(c_u32)]
     lib.lbft_set_seeds.argtypes = [P, P]

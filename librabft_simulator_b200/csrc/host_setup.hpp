@@ -87,7 +87,7 @@ struct HostSetup {
     if (c.num_nodes < 1 || c.num_nodes > 64) return fail("num_nodes must be in 1..64");
     if (!c.seeds) return fail("seeds must not be NULL");
     if (c.max_clock < 0 || c.max_clock >= (1 << 29)) return fail("max_clock must be in [0, 2^29)");
-    if (c.flags != 0) return fail("flags must be 0");
+    if (c.flags & ~(uint32_t)LBFT_FLAG_ROUND_SWITCHES) return fail("unknown bits in flags");
     if (c.commands_per_epoch == 0) return fail("commands_per_epoch must be > 0");
     if (c.delta < 0 || c.target_commit_interval < 0) return fail("delta and target_commit_interval must be >= 0");
     const uint32_t N = c.num_nodes;
@@ -138,7 +138,10 @@ struct HostSetup {
     // (explicit capacities beyond what the scan queue can encode / scan efficiently select the heap.)
     uint32_t qscan = (N <= 5 && c.max_clock < (1 << 24) - 64) ? 1u : 0u;
     if (c.payload_cap > 255 || c.queue_cap > 512) qscan = 0;
-    uint32_t qcap = c.queue_cap ? c.queue_cap : (qscan ? (N <= 4 ? 64u : 8 * N * N) : pow2_ceil(6 * N * N + 32));
+    // (recording round switches queues the duplicate timers the normal path elides — measured high-water marks
+    // roughly double, 46 -> 64+ at N = 4 — so the smallest committees get 128 entries and the HBM scan queue)
+    const bool record = (c.flags & LBFT_FLAG_ROUND_SWITCHES) != 0;
+    uint32_t qcap = c.queue_cap ? c.queue_cap : (qscan ? (N <= 4 ? (record ? 128u : 64u) : 8 * N * N) : pow2_ceil(6 * N * N + 32));
     if (2 * qcap < rcap && qscan) qcap = (rcap + 1) / 2;  // the read-out reuses the queue area as chain scratch
     if (qcap < rcap && !qscan) qcap = rcap;
     if (qcap > (1u << 20)) return fail("queue_cap too large");
@@ -154,7 +157,10 @@ struct HostSetup {
     // everything else with a moderate horizon: calendar queue (O(1) push/pop, exact: FIFO order inside a (time, kind)
     // list is creation-stamp order); the binary heap remains for long horizons
     if (qscan == 0 && c.max_clock <= 4095 && qcap <= 0xfff0u) qscan = 3;
-    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock);
+    // loop_until(.., Some(csv_path)) simulator.rs:380-381: keep DataWriter's round-switch table (the compile-time-layout
+    // kernel never records: its layout has no table, so the generic instantiation is selected)
+    p.record_rs = (c.flags & LBFT_FLAG_ROUND_SWITCHES) ? 1u : 0u;
+    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0);
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
     leader.resize(rcap + 1);
     for (uint32_t r = 0; r <= rcap; r++) leader[r] = (uint8_t)pick_author(weights, total, siphash13_u64(r));

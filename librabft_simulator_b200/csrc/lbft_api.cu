@@ -425,6 +425,31 @@ int lbft_commit_log(lbft_sim* s, uint32_t instance, uint32_t node, lbft_commit* 
   return LBFT_OK;
 }
 
+int lbft_round_switches(lbft_sim* s, uint32_t instance, lbft_round_switch* out, size_t cap, size_t* n) {
+  if (!s || !n) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  if (!s->P.record_rs) return set_error(LBFT_ERR_STATE, "round switches were not recorded: set LBFT_FLAG_ROUND_SWITCHES in lbft_config.flags");
+  if (!s->downloaded) return set_error(LBFT_ERR_STATE, "results are not available: call lbft_run first");
+  if (instance >= s->I) return set_error(LBFT_ERR_INVALID, "instance out of range");
+  if (cap && !out) return set_error(LBFT_ERR_INVALID, "out must not be NULL when cap > 0");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const Layout& L = s->P.L;
+  const uint32_t row = L.round_cap + 1;
+  std::vector<uint32_t> table((size_t)s->N * row);
+  const uint32_t tile = instance >> 5, lane = instance & 31;
+  const uint32_t* src = s->d_state + ((size_t)tile * L.total_words + rs_table_base(L)) * 32 + lane;
+  CUDA_TRY(cudaMemcpy2D(table.data(), sizeof(uint32_t), src, 32 * sizeof(uint32_t), sizeof(uint32_t), table.size(), cudaMemcpyDeviceToHost));
+  size_t k = 0;
+  for (uint32_t node = 0; node < s->N; node++)
+    for (uint32_t r = 0; r < row; r++) {
+      const uint32_t w = table[(size_t)node * row + r];
+      if (!w) continue;
+      if (k < cap) out[k] = lbft_round_switch{node, r, (int64_t)(w - 1u)};
+      k++;
+    }
+  *n = k;
+  return LBFT_OK;
+}
+
 void lbft_destroy(lbft_sim* s) { free_all(s); }
 
 }  // extern "C"

@@ -282,6 +282,7 @@ struct Core {
   uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify, dedup;
   uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
   uint32_t cal_t, cal_free, cal_next;  // QMODE 3: current bucket time, pool free list head, pool bump pointer
+  uint32_t rs_pend;  // recording only: node << 16 | active round of the round switch not yet stamped with a pop time (0: none)
   uint32_t cc0, cc1, cc2, cc3;  // chain cache: (round << 16) | previous QC round
 
   LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_, uint32_t* sk_ = nullptr,
@@ -1000,7 +1001,9 @@ struct Core {
     return push_event(t, kind, receiver | (sender << 8) | (slot << 16));
   }
   LBFT_HD void push_timer(uint32_t n, NodeRegs& d, int32_t t) {
-    if ((uint32_t)t == d.f[F_LAST_TIMER]) {
+    // (not while recording round switches: every pop is a DataWriter sampling point, data_writer.rs:34-50, so the
+    // duplicate has to be popped where the reference pops it)
+    if ((FIXED || !P.record_rs) && (uint32_t)t == d.f[F_LAST_TIMER]) {
       // An UpdateTimerEvent for (n, t) is already pending with a smaller stamp.  The duplicate could
       // only ever be popped right after it (same time) and be cancelled by
       // ignore_scheduled_updates_until (simulator.rs:403-410) with no side effect: account for it
@@ -1026,6 +1029,9 @@ struct Core {
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
     cal_t = 0; cal_free = PAY_NONE; cal_next = 0;
+    rs_pend = 0;
+    if (!FIXED && P.record_rs)
+      for (uint32_t w = 0; w < N * (L.round_cap + 1); w++) m.st(rs_table_base(L) + w, 0);
     if (QMODE == 3)
       for (uint32_t w = 0; w < (L.cal_times + 7) / 8; w++) m.st(L.cal_kmask + w, 0);
     for (uint32_t w = 0; w < N * L.node_words; w++) m.st(L.node_base + w, 0);
@@ -1072,6 +1078,14 @@ struct Core {
       uint32_t kind, data;
       pop_event(t, kind, data);
       if (t > P.max_clock) break;  // unreachable: such events are dropped at push
+      // DataWriter::update_round_number (data_writer.rs:34-50), called at simulator.rs:393-394 with the popped event's
+      // own scheduled time.  Only the node that handled the previous event can have a larger active round than at
+      // the previous pop, so at most one switch is pending.
+      if (!FIXED && P.record_rs && rs_pend) {
+        const uint32_t rn = rs_pend >> 16, rr = rs_pend & 0xffffu;
+        if (rr <= L.round_cap) m.st(rs_table_base(L) + rn * (L.round_cap + 1) + rr, (uint32_t)t + 1u);
+        rs_pend = 0;
+      }
       if (t > clock) clock = t;
       const uint32_t receiver = data & 0xffu, sender = (data >> 8) & 0xffu, slot = data >> 16;
       proc0 += kind == EV_NOTIFY;
@@ -1097,12 +1111,14 @@ struct Core {
       const bool is_request = kind == EV_REQUEST;  // answered by `receiver` itself (simulator.rs:446): no state change
       if (!is_request) {
         load_node(receiver, d);
+        const uint32_t pmr_before = d.f[F_PMR];
         if (kind == EV_TIMER && clock <= (int32_t)d.f[F_IGNORE]) {
           cancelled++;
           continue;
         }
         if (kind == EV_NOTIFY) should_sync = handle_notification(d, slot, sender);
         a = update_node(receiver, d, clock - (int32_t)d.f[F_STARTUP]);
+        if (!FIXED && P.record_rs && d.f[F_PMR] > pmr_before) rs_pend = (receiver << 16) | (d.f[F_PMR] & 0xffffu);
         // next UpdateTimerEvent, simulator.rs:311-324
         int64_t from_node = a.next == NODE_TIME_NEVER ? (int64_t)0x7fffffff : (int64_t)a.next + (int32_t)d.f[F_STARTUP];
         int64_t nt = from_node > (int64_t)clock + 1 ? from_node : (int64_t)clock + 1;

@@ -78,7 +78,7 @@ struct Layout {
 #define LBFT_LAYOUT_FN constexpr
 #endif
 LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
-                          uint32_t queue_scan, uint32_t max_clock = 0) {
+                          uint32_t queue_scan, uint32_t max_clock = 0, bool record_rs = false) {
   Layout L{};
   L.queue_scan = queue_scan;
   L.num_nodes = N;
@@ -120,9 +120,16 @@ LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue
   L.p_curhcbr = L.p_tchcbr + L.hcbr_words;
   L.pay_words = L.p_curhcbr + L.hcbr_words;
   L.pay_base = o; o += payload_cap * L.pay_words;
+  // DataWriter round-switch table (data_writer.rs:14), only when recording (LBFT_FLAG_ROUND_SWITCHES): [node][round 0..round_cap]
+  // = pop time + 1 (pops are at t >= 1; 0 = never seen), num_nodes * (round_cap + 1) words at the END of the instance, found
+  // with rs_table_base() — deliberately not a Layout field, so that Layout / Params keep the exact shape the
+  // compile-time-layout kernel was tuned with.
+  if (record_rs) o += N * (round_cap + 1);
   L.total_words = o;
   return L;
 }
+
+LBFT_LAYOUT_FN uint32_t rs_table_base(const Layout& L) { return L.pay_base + L.payload_cap * L.pay_words; }
 
 // Everything the kernel needs that is uniform over the launch.
 struct Params {
@@ -139,7 +146,7 @@ struct Params {
   uint32_t quorum;            // EpochConfiguration::quorum_threshold
   uint64_t silent_mask;
   uint32_t part_max_len;
-  uint32_t pad0;
+  uint32_t record_rs;        // LBFT_FLAG_ROUND_SWITCHES: keep the DataWriter round-switch table (takes the former pad word)
   double zig_r;
   uint32_t delay_kmax;       // > 0: delay_thr[k] (k = 0..delay_kmax) is valid and replaces exp() on the device
   uint32_t pad1;

@@ -13,6 +13,7 @@ advanced in lockstep on one B200); ``Simulator`` is the single-instance spelling
 simulation work happens in the CUDA library; this module only marshals arguments and results.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -137,8 +138,9 @@ class BatchSimulator:
 
     def __init__(self, seeds, num_nodes, network_delay=RandomDelay(), node_config=NodeConfig(),
                  commands_per_epoch=30000, voting_rights=None, silent=None, partition_windows=0,
-                 partition_max_len=0, device=0, round_cap=0, queue_cap=0, payload_cap=0):
+                 partition_max_len=0, device=0, round_cap=0, queue_cap=0, payload_cap=0, record_round_switches=False):
         self._lib = _lib.load()
+        self.record_round_switches = bool(record_round_switches)  # LBFT_FLAG_ROUND_SWITCHES (DataWriter, data_writer.rs)
         self.seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
         self.num_instances = int(self.seeds.shape[0])
         self.num_nodes = int(num_nodes)
@@ -168,6 +170,7 @@ class BatchSimulator:
         c.silent = None if self.silent is None else self.silent.ctypes.data
         c.partition_windows, c.partition_max_len = self.partition_windows, self.partition_max_len
         c.device, c.round_cap, c.queue_cap, c.payload_cap = self.device, self.round_cap, self.queue_cap, self.payload_cap
+        c.flags = _lib.FLAG_ROUND_SWITCHES if self.record_round_switches else 0
         return c
 
     def create(self, max_clock):
@@ -200,11 +203,17 @@ class BatchSimulator:
     def loop_until(self, max_clock, csv_path=None, strict=True):
         """``Simulator::new`` + ``loop_until(max_clock)`` for every instance; host buffers in, host results out."""
         if csv_path is not None:
-            raise NotImplementedError("DataWriter CSV output (data_writer.rs) is not part of the accelerated path")
+            # simulator.rs:380-381, 470-472: a DataWriter is kept during the loop and written at the end
+            if self.num_instances != 1:
+                raise ValueError("csv_path names ONE simulator's output directory: for a batch pass record_round_switches=True "
+                                 "and call write_data_files(path, instance)")
+            self.record_round_switches = True
         self.create(int(max_clock))
         code = self._lib.lbft_run(self._handle)
         _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
         self._read_timing()
+        if csv_path is not None:
+            self.write_data_files(csv_path, 0)
         return BatchResult(self)
 
     def set_seeds(self, seeds):
@@ -263,6 +272,53 @@ class BatchSimulator:
         buf = (_lib.LbftCommit * max(1, n.value))()
         _lib.check(self._lib.lbft_commit_log(self._handle, instance, author, buf, n.value, ctypes.byref(n)))
         return [(int(buf[i].proposer), int(buf[i].index), int(buf[i].time)) for i in range(n.value)]
+
+    def round_switches(self, instance):
+        """``DataWriter::nodes_round_switch`` of one instance as ``[(node, round, time)]``, node-major
+        (needs ``record_round_switches=True``)."""
+        n = ctypes.c_size_t(0)
+        _lib.check(self._lib.lbft_round_switches(self._handle, instance, None, 0, ctypes.byref(n)))
+        buf = (_lib.LbftRoundSwitch * max(1, n.value))()
+        _lib.check(self._lib.lbft_round_switches(self._handle, instance, buf, n.value, ctypes.byref(n)))
+        return [(int(buf[i].node), int(buf[i].round), int(buf[i].time)) for i in range(n.value)]
+
+    def write_data_files(self, path, instance=0):
+        """``DataWriter::new`` + ``write_to_file`` (data_writer.rs:20-33, 61-96) for one instance:
+        ``<path>/round_switches.txt`` and ``<path>/number_of_messages.txt``."""
+        counters = self._fetch("lbft_counters", np.uint32, (self.num_instances, 12))[instance]
+        write_data_files(path, self.num_nodes, self.round_switches(instance), int(counters[0]) + int(counters[1]) + int(counters[2]))
+
+
+def format_round_switches_csv(num_nodes, switches):
+    """Text of ``round_switches.txt`` (data_writer.rs:61-86) from ``[(node, round, time)]``.
+
+    A header ``node 0,node 1,..`` then one row per round in ``0..max_round`` — EXCLUSIVE of the largest round any
+    node reached, as the reference's ``for round_num in 0..max_round`` has it — holding, per node, the time at which
+    that round was first seen, or nothing.  Text conventions are the ``csv`` crate's defaults (bft-lib/Cargo.toml:23
+    ``csv = "1.1"``: ``,`` delimiter, ``\n`` terminator, quotes only when needed; a record that is a single empty field
+    is written as ``""``).  FORMAT UNPINNED: neither the crate nor a Rust toolchain is available here, so the bytes
+    are a restatement; the values are checked bit-exactly against the oracle, and the file is checked to read back
+    through the steps of the reference's own consumer (visualization/round_switch/round_plotter.py:11-14, 52-53).
+    """
+    first = {}
+    max_round = 0
+    for node, rnd, time in switches:
+        first.setdefault((node, rnd), time)  # `.find(..)`: the first entry of that round
+        max_round = max(max_round, rnd)
+    lines = [",".join("node %d" % n for n in range(num_nodes))]
+    for rnd in range(max_round):
+        fields = ["" if (n, rnd) not in first else str(first[(n, rnd)]) for n in range(num_nodes)]
+        lines.append('""' if fields == [""] else ",".join(fields))
+    return "\n".join(lines) + "\n"
+
+
+def write_data_files(path, num_nodes, switches, message_count):
+    if not os.path.exists(path):
+        os.mkdir(path)  # fs::create_dir: not recursive (data_writer.rs:28-30)
+    with open(os.path.join(path, "round_switches.txt"), "w", newline="") as f:
+        f.write(format_round_switches_csv(num_nodes, switches))
+    with open(os.path.join(path, "number_of_messages.txt"), "w", newline="") as f:
+        f.write("%d\n" % message_count)  # wtr.serialize(Some(message_counter)) data_writer.rs:88-95
 
 
 class Simulator:

@@ -1278,12 +1278,36 @@ struct Simulator {
     }
   }
 
+  // DataWriter state (data_writer.rs:10-17), kept when loop_until is given a csv path (simulator.rs:381).
+  // PARITY UNPINNED for this output: the reference has no test or golden for DataWriter; the event
+  // sequence it samples is pinned by the commit-log goldens.
+  bool record_round_switches = false;
+  std::vector<uint64_t> max_round_per_node;                                     // :13
+  std::vector<std::vector<std::pair<uint64_t, int64_t>>> nodes_round_switch;   // :14
+  // update_round_number data_writer.rs:34-50 — every node is looked at, at every pop.
+  void sample_round_numbers(int64_t scheduled_time) {
+    if (max_round_per_node.size() != nodes.size()) {
+      max_round_per_node.assign(nodes.size(), 0);
+      nodes_round_switch.assign(nodes.size(), {});
+    }
+    for (size_t n = 0; n < nodes.size(); n++) {
+      uint64_t r = nodes[n].node.active_round();
+      if (r > max_round_per_node[n]) {
+        max_round_per_node[n] = r;
+        nodes_round_switch[n].push_back({r, scheduled_time});
+      }
+    }
+  }
+
   // loop_until :380-475
   void loop_until(int64_t max_clock) {
     while (!pending_events.empty()) {
       Event ev = pending_events.top();
       pending_events.pop();
       if (ev.time > max_clock) break;
+      // :393-394 — after the max_clock test, with the event's own scheduled_time (the max() with the
+      // simulator clock comes later, :399), and before the timer-cancellation test (:406).
+      if (record_round_switches) sample_round_numbers(ev.time);
       int64_t clk = std::max(ev.time, clock);
       clock = clk;
       counters.processed[ev.kind]++;

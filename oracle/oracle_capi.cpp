@@ -49,12 +49,21 @@ static void make_partition_plan(const lbft_config* c, uint64_t seed, SimConfig& 
 
 static void run_one(const lbft_config* c, const SimConfig& base, uint32_t inst, uint32_t* commit_counts,
                     uint64_t* last_states, lbft_instance_counters* counters, uint32_t* status,
-                    std::vector<std::vector<CommitEntry>>* logs) {
+                    std::vector<std::vector<CommitEntry>>* logs, std::vector<lbft_round_switch>* switches = nullptr) {
   SimConfig s = base;
   uint64_t seed = c->seeds[inst];
   make_partition_plan(c, seed, s);
   uint32_t st = 0;
   Simulator sim(seed, s);
+  sim.record_round_switches = switches != nullptr;
+  struct Collect {  // node-major, rounds ascending within a node (the order of include/lbft.h)
+    Simulator& sim; std::vector<lbft_round_switch>* out;
+    ~Collect() {
+      if (!out) return;
+      for (size_t n = 0; n < sim.nodes_round_switch.size(); n++)
+        for (auto& e : sim.nodes_round_switch[n]) out->push_back(lbft_round_switch{(uint32_t)n, (uint32_t)e.first, e.second});
+    }
+  } collect{sim, switches};
   try {
     sim.loop_until(s.max_clock);
     st |= LBFT_ST_DONE;
@@ -127,6 +136,18 @@ int lbfo_commit_log(const lbft_config* c, uint32_t instance, uint32_t node, lbft
   const auto& h = logs[node];
   if (n) *n = h.size();
   for (size_t i = 0; i < h.size() && i < cap; i++) out[i] = lbft_commit{h[i].proposer, h[i].index, h[i].time};
+  return LBFT_OK;
+}
+
+// Round switches of one instance, as DataWriter would have collected them (data_writer.rs:34-50).
+int lbfo_round_switches(const lbft_config* c, uint32_t instance, lbft_round_switch* out, size_t cap, size_t* n) {
+  SimConfig base;
+  if (!make_cfg(c, base, g_err)) return LBFT_ERR_INVALID;
+  if (instance >= c->num_instances) { g_err = "index out of range"; return LBFT_ERR_INVALID; }
+  std::vector<lbft_round_switch> sw;
+  run_one(c, base, instance, nullptr, nullptr, nullptr, nullptr, nullptr, &sw);
+  if (n) *n = sw.size();
+  for (size_t i = 0; i < sw.size() && i < cap; i++) out[i] = sw[i];
   return LBFT_OK;
 }
 

@@ -26,6 +26,10 @@ static void run_all(const Params& P, std::vector<uint32_t>& state, const double*
   }
 }
 
+static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
+                    uint32_t* counters, uint32_t* status, uint32_t* words_per_instance, std::vector<uint32_t>& state,
+                    Params& P);
+
 extern "C" {
 const char* hostcore_last_error(void) { return g_err.c_str(); }
 
@@ -47,9 +51,43 @@ int hostcore_setup_info(const lbft_config* c, uint32_t* out6) {
 // round_cap * 2 words of the chain table and leader_out (optional) the leader table.
 int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
                  uint32_t* counters, uint32_t* status, uint32_t* words_per_instance) {
+  std::vector<uint32_t> state;
+  Params P;
+  return run_impl(c, commit_counts, last_states, lc_round, counters, status, words_per_instance, state, P);
+}
+
+// Same contract as the product's lbft_round_switches (include/lbft.h): runs the batch with the configuration's
+// flags (LBFT_FLAG_ROUND_SWITCHES required) and reads one instance's table out of the tile layout.
+int hostcore_round_switches(const lbft_config* c, uint32_t instance, lbft_round_switch* out, size_t cap, size_t* n) {
+  if (!(c->flags & LBFT_FLAG_ROUND_SWITCHES)) { g_err = "LBFT_FLAG_ROUND_SWITCHES not set"; return LBFT_ERR_STATE; }
+  if (instance >= c->num_instances) { g_err = "instance out of range"; return LBFT_ERR_INVALID; }
+  const size_t IN = (size_t)c->num_instances * c->num_nodes;
+  std::vector<uint32_t> cc(IN), lc(IN), counters((size_t)c->num_instances * 12), status(c->num_instances), state;
+  std::vector<uint64_t> ls(IN);
+  Params P;
+  int rc = run_impl(c, cc.data(), ls.data(), lc.data(), counters.data(), status.data(), nullptr, state, P);
+  if (rc != LBFT_OK) return rc;
+  const Layout& L = P.L;
+  const uint32_t row = L.round_cap + 1, tile = instance >> 5, lane = instance & 31;
+  size_t k = 0;
+  for (uint32_t node = 0; node < c->num_nodes; node++)
+    for (uint32_t r = 0; r < row; r++) {
+      const uint32_t w = state[((size_t)tile * L.total_words + rs_table_base(L) + (size_t)node * row + r) * 32 + lane];
+      if (!w) continue;
+      if (k < cap) out[k] = lbft_round_switch{node, r, (int64_t)(w - 1u)};
+      k++;
+    }
+  if (n) *n = k;
+  return LBFT_OK;
+}
+}  // extern "C"
+
+static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
+                    uint32_t* counters, uint32_t* status, uint32_t* words_per_instance, std::vector<uint32_t>& state,
+                    Params& P) {
   HostSetup hs;
   if (!hs.build(*c)) { g_err = hs.error; return LBFT_ERR_INVALID; }
-  Params P = hs.params;
+  P = hs.params;
   P.seeds = c->seeds;
   P.zig_x = hs.zig_x.data();
   P.zig_f = hs.zig_f.data();
@@ -59,7 +97,7 @@ int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_s
   P.weights = hs.weights.data();
   P.delay_thr = hs.delay_thr.empty() ? nullptr : hs.delay_thr.data();
   uint32_t tiles = (c->num_instances + 31) / 32;
-  std::vector<uint32_t> state((size_t)tiles * P.L.total_words * 32, 0xdeadbeefu);
+  state.assign((size_t)tiles * P.L.total_words * 32, 0xdeadbeefu);
   P.state = state.data();
   P.out_commit_counts = commit_counts;
   P.out_last_state = last_states;
@@ -79,5 +117,4 @@ int hostcore_run(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_s
   else RUN(64, 0);
 #undef RUN
   return LBFT_OK;
-}
 }

@@ -48,6 +48,27 @@ class Result:
         self.seconds = 0.0
 
 
+class LbftRoundSwitch(ctypes.Structure):
+    """include/lbft.h lbft_round_switch"""
+    _fields_ = [("node", ctypes.c_uint32), ("round", ctypes.c_uint32), ("time", ctypes.c_int64)]
+
+
+FLAG_ROUND_SWITCHES = 1
+
+
+def _round_switches(fn, err, seeds, num_nodes, instance, max_clock, **kw):
+    """Calls an (cfg, instance, out, cap, n) entry point twice (size, then data); returns [(node, round, time)]."""
+    kw.setdefault("flags", FLAG_ROUND_SWITCHES)
+    cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
+    n = ctypes.c_size_t()
+    if fn(ctypes.byref(cfg), instance, None, 0, ctypes.byref(n)) != 0:
+        raise RuntimeError(err().decode())
+    buf = (LbftRoundSwitch * max(n.value, 1))()
+    if fn(ctypes.byref(cfg), instance, buf, n.value, ctypes.byref(n)) != 0:
+        raise RuntimeError(err().decode())
+    return [(buf[i].node, buf[i].round, buf[i].time) for i in range(n.value)]
+
+
 class Oracle:
     def __init__(self):
         path = _build.build_oracle()
@@ -90,6 +111,13 @@ class Oracle:
             raise RuntimeError(self.lib.lbfo_last_error().decode())
         res.seconds = sec.value
         return res
+
+    def round_switches(self, seeds, num_nodes, instance, max_clock=1000, **kw):
+        """DataWriter::nodes_round_switch of one instance (data_writer.rs:34-50), node-major."""
+        fn = self.lib.lbfo_round_switches
+        fn.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t,
+                       ctypes.POINTER(ctypes.c_size_t)]
+        return _round_switches(fn, self.lib.lbfo_last_error, seeds, num_nodes, instance, max_clock, **kw)
 
     def commit_log(self, seeds, num_nodes, instance, node, max_clock=1000, **kw):
         cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
@@ -141,6 +169,12 @@ class HostCore:
             raise RuntimeError(self.lib.hostcore_last_error().decode())
         res.words_per_instance = w.value
         return res
+
+    def round_switches(self, seeds, num_nodes, instance, max_clock=1000, **kw):
+        fn = self.lib.hostcore_round_switches
+        fn.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t,
+                       ctypes.POINTER(ctypes.c_size_t)]
+        return _round_switches(fn, self.lib.hostcore_last_error, seeds, num_nodes, instance, max_clock, **kw)
 
 
 def assert_same(a, b, what=""):
