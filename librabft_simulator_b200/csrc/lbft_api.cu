@@ -44,7 +44,7 @@ struct LaunchShape {
   static constexpr int kBlocksPerSm = QMODE == 2 ? 7 : 14;
 };
 
-template <int NMAX, int QMODE, bool FIXED = false>
+template <int NMAX, int QMODE, bool FIXED = false, bool REC = false>
 __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<32>, NMAX, QMODE, FIXED> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  Core<TileMem<32>, NMAX, QMODE, FIXED, REC> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
@@ -288,13 +288,14 @@ int lbft_run_device(lbft_sim* s) {
     constexpr int T = LaunchShape<QM>::kThreads;                                                                   \
     const uint32_t blocks = (s->I + T - 1) / T;                                                                    \
     const size_t dyn = QM == 2 ? (size_t)(T / 32) * s->P.L.queue_cap * (32 * 4 + 32 * 2) : 0;                      \
-    lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, s->stream>>>(s->P);                                        \
+    if (s->P.record_rs) lbft_event_loop_kernel<NMAX, QM, false, true><<<blocks, T, dyn, s->stream>>>(s->P);       \
+    else lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, s->stream>>>(s->P);                                   \
   } while (0)
   // the default four-author layout has a kernel instantiation with compile-time field offsets
   constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
   const bool plain_model = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0 &&
                            s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
-  if (s->P.L.queue_scan == 2 && plain_model && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
+  if (s->P.L.queue_scan == 2 && plain_model && !s->P.record_rs && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
     constexpr int T = LaunchShape<2>::kThreads;
     lbft_event_loop_kernel<16, 2, true><<<(s->I + T - 1) / T, T, (size_t)(T / 32) * 64 * (32 * 4 + 32 * 2), s->stream>>>(s->P);
   } else if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);

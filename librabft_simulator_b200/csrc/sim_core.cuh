@@ -260,8 +260,12 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // default capacities) instead of the launch parameter block: every field offset folds into an immediate.  The host
 // only selects it for the reference's own model (LogNormal delay served by the threshold table, no silent nodes, no
 // partitions), so those extension branches are compiled out as well.
-template <class Mem, int NMAX, int QMODE, bool FIXED = false>
+// REC: keep DataWriter's round-switch table (LBFT_FLAG_ROUND_SWITCHES, Params::record_rs).  A template parameter rather
+// than a run-time test so that the non-recording instantiations carry no trace of it (the run-time test measured
+// +0.8..2.0 % on the generic kernels, profiles/README.md).
+template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false>
 struct Core {
+  static_assert(!(FIXED && REC), "the compile-time layout has no round-switch table");
   static constexpr int S = Mem::STRIDE;
   const Params& P;
   const Layout L;
@@ -1003,7 +1007,7 @@ struct Core {
   LBFT_HD void push_timer(uint32_t n, NodeRegs& d, int32_t t) {
     // (not while recording round switches: every pop is a DataWriter sampling point, data_writer.rs:34-50, so the
     // duplicate has to be popped where the reference pops it)
-    if ((FIXED || !P.record_rs) && (uint32_t)t == d.f[F_LAST_TIMER]) {
+    if (!REC && (uint32_t)t == d.f[F_LAST_TIMER]) {
       // An UpdateTimerEvent for (n, t) is already pending with a smaller stamp.  The duplicate could
       // only ever be popped right after it (same time) and be cancelled by
       // ignore_scheduled_updates_until (simulator.rs:403-410) with no side effect: account for it
@@ -1029,9 +1033,10 @@ struct Core {
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
     cal_t = 0; cal_free = PAY_NONE; cal_next = 0;
-    rs_pend = 0;
-    if (!FIXED && P.record_rs)
+    if (REC) {
+      rs_pend = 0;
       for (uint32_t w = 0; w < N * (L.round_cap + 1); w++) m.st(rs_table_base(L) + w, 0);
+    }
     if (QMODE == 3)
       for (uint32_t w = 0; w < (L.cal_times + 7) / 8; w++) m.st(L.cal_kmask + w, 0);
     for (uint32_t w = 0; w < N * L.node_words; w++) m.st(L.node_base + w, 0);
@@ -1081,7 +1086,7 @@ struct Core {
       // DataWriter::update_round_number (data_writer.rs:34-50), called at simulator.rs:393-394 with the popped event's
       // own scheduled time.  Only the node that handled the previous event can have a larger active round than at
       // the previous pop, so at most one switch is pending.
-      if (!FIXED && P.record_rs && rs_pend) {
+      if (REC && rs_pend) {
         const uint32_t rn = rs_pend >> 16, rr = rs_pend & 0xffffu;
         if (rr <= L.round_cap) m.st(rs_table_base(L) + rn * (L.round_cap + 1) + rr, (uint32_t)t + 1u);
         rs_pend = 0;
@@ -1118,7 +1123,7 @@ struct Core {
         }
         if (kind == EV_NOTIFY) should_sync = handle_notification(d, slot, sender);
         a = update_node(receiver, d, clock - (int32_t)d.f[F_STARTUP]);
-        if (!FIXED && P.record_rs && d.f[F_PMR] > pmr_before) rs_pend = (receiver << 16) | (d.f[F_PMR] & 0xffffu);
+        if (REC && d.f[F_PMR] > pmr_before) rs_pend = (receiver << 16) | (d.f[F_PMR] & 0xffffu);
         // next UpdateTimerEvent, simulator.rs:311-324
         int64_t from_node = a.next == NODE_TIME_NEVER ? (int64_t)0x7fffffff : (int64_t)a.next + (int32_t)d.f[F_STARTUP];
         int64_t nt = from_node > (int64_t)clock + 1 ? from_node : (int64_t)clock + 1;

@@ -12,14 +12,14 @@
 using namespace lbft;
 static thread_local std::string g_err;
 
-template <int NMAX, int QMODE>
+template <int NMAX, int QMODE, bool REC>
 static void run_all(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
     std::vector<uint32_t> sk(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);  // stands in for the shared-memory queue
     std::vector<uint16_t> sd(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);
-    Core<TileMem<32>, NMAX, QMODE> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
+    Core<TileMem<32>, NMAX, QMODE, false, REC> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
     core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);
@@ -105,7 +105,7 @@ static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* las
   P.out_counters = counters;
   P.out_status = status;
   if (words_per_instance) *words_per_instance = P.L.total_words;
-#define RUN(NMAX, QS) run_all<NMAX, QS>(P, state, P.zig_x, P.zig_f)
+#define RUN(NMAX, QS) (P.record_rs ? run_all<NMAX, QS, true>(P, state, P.zig_x, P.zig_f) : run_all<NMAX, QS, false>(P, state, P.zig_x, P.zig_f))
   if (P.L.queue_scan == 2) RUN(16, 2);
   else if (P.L.queue_scan == 1) RUN(16, 1);
   else if (P.L.queue_scan == 3) {

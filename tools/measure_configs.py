@@ -17,6 +17,7 @@ CONFIGS = [
     ("config2 1024x4 LogNormal(10,4)", 1024, 4, RandomDelay.new(10.0, 4.0), {}, {}),
     ("config2 1024x4 uniform[5,15]", 1024, 4, RandomDelay.uniform(5, 15), {}, {"delay_kind": 1, "delay_lo": 5, "delay_hi": 15}),
     ("config3 65536x4 LogNormal(10,4)", 65536, 4, RandomDelay.new(10.0, 4.0), {}, {}),
+    ("config3 65536x4 + round-switch recording (flag)", 65536, 4, RandomDelay.new(10.0, 4.0), {"record_round_switches": True}, {}),
     ("config5 16384x7 partitions(4 windows <=150ms)", 16384, 7, RandomDelay.new(10.0, 4.0),
      {"partition_windows": 4, "partition_max_len": 150}, {"partition_windows": 4, "partition_max_len": 150}),
     ("config4 8192x64 weighted, 21 silent", 8192, 64, RandomDelay.new(10.0, 4.0),
@@ -36,6 +37,8 @@ for name, I, N, delay, kw, okw in CONFIGS:
     sample = [0, I // 2, I - 1]
     ref = oracle.run(seeds[sample], N, 1000, **okw)
     ok = (ref.last_states == res.last_committed_states[sample]).all() and (ref.counters[:, :8] == res.counters[sample, :8]).all()
+    if kw.get("record_round_switches"):  # the recorded switches of the sampled instances, too
+        ok = ok and all(sim.round_switches(i) == oracle.round_switches(seeds[[i]], N, 0, 1000, **okw) for i in sample)
     print("%-48s kernel %9.2f ms  e2e %9.2f ms  %8.2f Mrounds/s  %7.3f Gev/s  state %6.1f KB/inst (%5.2f GB)  status %s  "
           "maxq %d maxpay %d  oracle-sample %s" % (name, ms, wall * 1e3, rounds / ms / 1e3, events / ms / 1e6, words * 4 / 1024,
                                                    dev_bytes / 1e9, np.unique(res.status).tolist(), res.counters[:, 8].max(),
