@@ -13,6 +13,8 @@
 //   * bft-lib/src/unit_tests/configuration_tests.rs:6-47 (pick_author KAT, quorum thresholds)
 //   * librabft-v2/src/unit_tests/record_store_tests.rs:106-292 (scripted record-store sequences)
 //   * bft-lib/src/unit_tests/simulated_context_tests.rs:79-129, README.md:27 (empty-log state key)
+// PARITY UNPINNED for one output: the DataWriter round-switch log (sample_round_numbers, data_writer.rs:34-50) has no
+// test, golden or fixture in the reference; it is a reading of the source over the (pinned) event sequence.
 // Third-party arithmetic that is NOT under /root/reference (semver pins from bft-lib/Cargo.toml:18-21,
 // no lockfile): rand 0.8.3 (gen_range, shuffle), rand_distr 0.4.0 (LogNormal / ziggurat normal),
 // rand_xoshiro 0.6.0 (SplitMix64 seeding, Xoshiro256**), Rust std DefaultHasher (SipHash-1-3, zero
