@@ -75,6 +75,7 @@ typedef struct lbft_round_switch {
 
 /* lbft_config.flags */
 #define LBFT_FLAG_ROUND_SWITCHES 1u /* record round switches = loop_until(.., Some(csv_path)) simulator.rs:380-381 */
+#define LBFT_FLAG_RESUMABLE 2u      /* lbft_run_until / snapshots: loop_until may be called again with a larger clock   */
 
 /* Per-instance event counters (simulator.rs:31 event_count; data_writer.rs message counter). */
 typedef struct lbft_instance_counters {
@@ -170,6 +171,21 @@ int lbft_status(lbft_sim* sim, uint32_t* out);
 int lbft_timing_info(lbft_sim* sim, lbft_timing* out);
 /* Bytes of device memory held by the handle, and the per-instance state footprint. */
 int lbft_memory_info(lbft_sim* sim, uint64_t* device_bytes, uint32_t* words_per_instance);
+
+/* Resumable runs (needs LBFT_FLAG_RESUMABLE, else LBFT_ERR_STATE).  lbft_config.max_clock is the FINAL horizon the
+ * device tables are sized for; lbft_run_until(sim, t), 0 <= t <= max_clock, is loop_until(GlobalTime(t), ..)
+ * (simulator.rs:380-475) on every instance: the first call is Simulator::new + loop_until, each later call continues
+ * where the previous one stopped — including the reference's own exit behaviour: the first event beyond t is popped
+ * and dropped (simulator.rs:383-391), so a staged run is NOT the same simulation as a one-shot run to the same
+ * clock.  Results (all getters) describe the state at the stop.  lbft_run / lbft_upload / lbft_set_seeds start over. */
+int lbft_run_until(lbft_sim* sim, int64_t stop_clock);
+/* Checkpoint of the whole batch between two lbft_run_until calls (the batched analogue of
+ * ConsensusNode::save_node / load_node, librabft-v2/src/node.rs:211-238, plus the simulator's own queue, clock and
+ * RNG): save after a lbft_run_until, load into a handle created from the same configuration (verified by a digest;
+ * LBFT_ERR_INVALID otherwise), then continue with lbft_run_until. */
+int lbft_snapshot_size(lbft_sim* sim, size_t* bytes);
+int lbft_snapshot_save(lbft_sim* sim, void* buf, size_t cap);
+int lbft_snapshot_load(lbft_sim* sim, const void* buf, size_t bytes);
 
 /* Device address of a result buffer, for callers that consume results on the GPU (e.g. an NCCL
  * all-gather of per-instance commit counts): which = 0 commit counts [I][N] u32, 1 last states [I][N]

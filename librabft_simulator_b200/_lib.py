@@ -34,6 +34,7 @@ class LbftRoundSwitch(ctypes.Structure):
 
 
 FLAG_ROUND_SWITCHES = 1  # LBFT_FLAG_ROUND_SWITCHES
+FLAG_RESUMABLE = 2  # LBFT_FLAG_RESUMABLE
 
 
 class LbftTiming(ctypes.Structure):
@@ -50,7 +51,7 @@ ST_ERROR_MASK = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST
 EXPORTS = [
     "lbft_create", "lbft_run", "lbft_upload", "lbft_run_device", "lbft_download", "lbft_commit_counts",
     "lbft_last_states", "lbft_commit_log", "lbft_round_switches", "lbft_counters", "lbft_status", "lbft_timing_info",
-    "lbft_memory_info", "lbft_set_seeds", "lbft_device_buffer", "lbft_destroy", "lbft_last_error", "lbft_abi_version",
+    "lbft_memory_info", "lbft_run_until", "lbft_snapshot_size", "lbft_snapshot_save", "lbft_snapshot_load", "lbft_set_seeds", "lbft_device_buffer", "lbft_destroy", "lbft_last_error", "lbft_abi_version",
 ]
 
 _lib = None
@@ -81,6 +82,10 @@ def load():
     lib.lbft_commit_log.argtypes = [P, c_u32, c_u32, ctypes.POINTER(LbftCommit), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.lbft_round_switches.argtypes = [P, c_u32, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.lbft_timing_info.argtypes = [P, ctypes.POINTER(LbftTiming)]
+    lib.lbft_run_until.argtypes = [P, c_i64]
+    lib.lbft_snapshot_size.argtypes = [P, ctypes.POINTER(ctypes.c_size_t)]
+    lib.lbft_snapshot_save.argtypes = [P, P, ctypes.c_size_t]
+    lib.lbft_snapshot_load.argtypes = [P, P, ctypes.c_size_t]
     lib.lbft_memory_info.argtypes = [P, ctypes.POINTER(c_u64), ctypes.POINTER(c_u32)]
     lib.lbft_set_seeds.argtypes = [P, P]
     lib.lbft_device_buffer.argtypes = [P, c_u32, ctypes.POINTER(P), ctypes.POINTER(ctypes.c_size_t)]

@@ -87,7 +87,7 @@ struct HostSetup {
     if (c.num_nodes < 1 || c.num_nodes > 64) return fail("num_nodes must be in 1..64");
     if (!c.seeds) return fail("seeds must not be NULL");
     if (c.max_clock < 0 || c.max_clock >= (1 << 29)) return fail("max_clock must be in [0, 2^29)");
-    if (c.flags & ~(uint32_t)LBFT_FLAG_ROUND_SWITCHES) return fail("unknown bits in flags");
+    if (c.flags & ~(uint32_t)(LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE)) return fail("unknown bits in flags");
     if (c.commands_per_epoch == 0) return fail("commands_per_epoch must be > 0");
     if (c.delta < 0 || c.target_commit_interval < 0) return fail("delta and target_commit_interval must be >= 0");
     const uint32_t N = c.num_nodes;
@@ -140,7 +140,8 @@ struct HostSetup {
     if (c.payload_cap > 255 || c.queue_cap > 512) qscan = 0;
     // (recording round switches queues the duplicate timers the normal path elides — measured high-water marks
     // roughly double, 46 -> 64+ at N = 4 — so the smallest committees get 128 entries and the HBM scan queue)
-    const bool record = (c.flags & LBFT_FLAG_ROUND_SWITCHES) != 0;
+    // (resumable runs queue them too: the event dropped at a stop must be the one the reference drops)
+    const bool record = (c.flags & (LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE)) != 0;
     uint32_t qcap = c.queue_cap ? c.queue_cap : (qscan ? (N <= 4 ? (record ? 128u : 64u) : 8 * N * N) : pow2_ceil(6 * N * N + 32));
     if (2 * qcap < rcap && qscan) qcap = (rcap + 1) / 2;  // the read-out reuses the queue area as chain scratch
     if (qcap < rcap && !qscan) qcap = rcap;
@@ -160,7 +161,10 @@ struct HostSetup {
     // loop_until(.., Some(csv_path)) simulator.rs:380-381: keep DataWriter's round-switch table (the compile-time-layout
     // kernel never records: its layout has no table, so the generic instantiation is selected)
     p.record_rs = (c.flags & LBFT_FLAG_ROUND_SWITCHES) ? 1u : 0u;
-    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0);
+    p.resumable = (c.flags & LBFT_FLAG_RESUMABLE) ? 1u : 0u;
+    p.stop_clock = p.max_clock;
+    p.run_flags = 0;
+    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0);
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
     leader.resize(rcap + 1);
     for (uint32_t r = 0; r <= rcap; r++) leader[r] = (uint8_t)pick_author(weights, total, siphash13_u64(r));

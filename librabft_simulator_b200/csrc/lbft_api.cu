@@ -44,7 +44,7 @@ struct LaunchShape {
   static constexpr int kBlocksPerSm = QMODE == 2 ? 7 : 14;
 };
 
-template <int NMAX, int QMODE, bool FIXED = false, bool REC = false>
+template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false>
 __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
@@ -73,10 +73,12 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<32>, NMAX, QMODE, FIXED, REC> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
-  core.init(P.seeds[inst]);
+  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
+  else core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
+  if (RES) core.save_regs();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -126,6 +128,9 @@ struct lbft_sim {
   uint32_t* h_counters = nullptr;
   uint32_t* h_status = nullptr;
   bool uploaded = false, ran = false, downloaded = false;
+  bool started = false;     // resumable handles: a staged run is in progress, the next launch restores the instances
+  int64_t next_stop = 0;    // stop clock of the next launch (max_clock unless set by lbft_run_until)
+  int64_t last_stop = -1;   // stop clock of the last launch
   lbft_timing timing{};
 };
 
@@ -247,6 +252,7 @@ int lbft_set_seeds(lbft_sim* s, const uint64_t* seeds) {
   if (!s || !seeds) return set_error(LBFT_ERR_INVALID, "NULL argument");
   memcpy(s->h_seeds, seeds, (size_t)s->I * sizeof(uint64_t));
   s->uploaded = false;
+  s->started = false;
   return LBFT_OK;
 }
 
@@ -275,6 +281,8 @@ int lbft_upload(lbft_sim* s) {
   s->timing.h2d_ms = ms;
   s->timing.h2d_bytes = s->I * sizeof(uint64_t);
   s->uploaded = true;
+  s->started = false;  // fresh seeds: the next launch is Simulator::new
+  s->next_stop = s->P.max_clock;
   return LBFT_OK;
 }
 
@@ -282,20 +290,24 @@ int lbft_run_device(lbft_sim* s) {
   if (!s) return set_error(LBFT_ERR_INVALID, "sim must not be NULL");
   if (!s->uploaded) return set_error(LBFT_ERR_STATE, "lbft_upload must be called before lbft_run_device");
   CUDA_TRY(cudaSetDevice(s->device));
+  s->P.stop_clock = (int32_t)(s->P.resumable ? s->next_stop : (int64_t)s->P.max_clock);
+  s->P.run_flags = (s->P.resumable && s->started) ? 1u : 0u;
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
 #define LBFT_LAUNCH(NMAX, QM)                                                                                      \
   do {                                                                                                             \
     constexpr int T = LaunchShape<QM>::kThreads;                                                                   \
     const uint32_t blocks = (s->I + T - 1) / T;                                                                    \
     const size_t dyn = QM == 2 ? (size_t)(T / 32) * s->P.L.queue_cap * (32 * 4 + 32 * 2) : 0;                      \
-    if (s->P.record_rs) lbft_event_loop_kernel<NMAX, QM, false, true><<<blocks, T, dyn, s->stream>>>(s->P);       \
-    else lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, s->stream>>>(s->P);                                   \
+    if (s->P.record_rs && s->P.resumable) lbft_event_loop_kernel<NMAX, QM, false, true, true><<<blocks, T, dyn, s->stream>>>(s->P); \
+    else if (s->P.resumable) lbft_event_loop_kernel<NMAX, QM, false, false, true><<<blocks, T, dyn, s->stream>>>(s->P);          \
+    else if (s->P.record_rs) lbft_event_loop_kernel<NMAX, QM, false, true><<<blocks, T, dyn, s->stream>>>(s->P);                 \
+    else lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, s->stream>>>(s->P);                                                   \
   } while (0)
   // the default four-author layout has a kernel instantiation with compile-time field offsets
   constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
   const bool plain_model = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0 &&
                            s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
-  if (s->P.L.queue_scan == 2 && plain_model && !s->P.record_rs && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
+  if (s->P.L.queue_scan == 2 && plain_model && !s->P.record_rs && !s->P.resumable && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
     constexpr int T = LaunchShape<2>::kThreads;
     lbft_event_loop_kernel<16, 2, true><<<(s->I + T - 1) / T, T, (size_t)(T / 32) * 64 * (32 * 4 + 32 * 2), s->stream>>>(s->P);
   } else if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);
@@ -319,6 +331,8 @@ int lbft_run_device(lbft_sim* s) {
   s->timing.kernel_launches = 1;
   s->ran = true;
   s->downloaded = false;
+  s->started = s->P.resumable != 0;
+  s->last_stop = s->P.stop_clock;
   return LBFT_OK;
 }
 
@@ -356,6 +370,89 @@ int lbft_run(lbft_sim* s) {
   r = lbft_run_device(s);
   if (r != LBFT_OK) return r;
   return lbft_download(s);
+}
+
+int lbft_run_until(lbft_sim* s, int64_t stop_clock) {
+  if (!s) return set_error(LBFT_ERR_INVALID, "sim must not be NULL");
+  if (!s->P.resumable) return set_error(LBFT_ERR_STATE, "not a resumable handle: set LBFT_FLAG_RESUMABLE in lbft_config.flags");
+  if (stop_clock < 0 || stop_clock > s->P.max_clock)
+    return set_error(LBFT_ERR_INVALID, "stop_clock must be in [0, lbft_config.max_clock] (the horizon the device tables are sized for)");
+  if (!s->started) {
+    int r = lbft_upload(s);  // Simulator::new on the next launch
+    if (r != LBFT_OK) return r;
+  }
+  s->next_stop = stop_clock;
+  int r = lbft_run_device(s);
+  if (r != LBFT_OK) return r;
+  return lbft_download(s);
+}
+
+// ---- snapshots: header + the state tiles (which hold the save areas of a resumable handle) ----
+namespace {
+struct SnapshotHeader {
+  uint64_t magic;  // "LBFTSNP1"
+  uint32_t abi, num_instances, num_nodes, total_words;
+  int64_t max_clock, last_stop;
+  uint64_t config_digest;
+};
+constexpr uint64_t kSnapMagic = 0x31504e535446424cULL;
+uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ULL; }
+  return h;
+}
+// Everything that shapes the simulation except the seeds: the scalar part of Params (layout, delay model, quorum,
+// voting rights, ...) and the host tables.
+uint64_t config_digest(const lbft_sim* s) {
+  Params q = s->P;
+  q.stop_clock = 0; q.run_flags = 0;
+  uint64_t h = fnv1a(0xcbf29ce484222325ULL, &q, offsetof(Params, seeds));
+  h = fnv1a(h, s->hs.leader.data(), s->hs.leader.size());
+  h = fnv1a(h, s->hs.duration.data(), s->hs.duration.size() * sizeof(int32_t));
+  h = fnv1a(h, s->hs.period.data(), s->hs.period.size() * sizeof(int32_t));
+  if (!s->hs.delay_thr.empty()) h = fnv1a(h, s->hs.delay_thr.data(), s->hs.delay_thr.size() * sizeof(double));
+  return h;
+}
+size_t state_bytes(const lbft_sim* s) { return (size_t)((s->I + 31) / 32) * s->P.L.total_words * 32 * sizeof(uint32_t); }
+}  // namespace
+
+int lbft_snapshot_size(lbft_sim* s, size_t* bytes) {
+  if (!s || !bytes) return set_error(LBFT_ERR_INVALID, "NULL argument");
+  if (!s->P.resumable) return set_error(LBFT_ERR_STATE, "not a resumable handle: set LBFT_FLAG_RESUMABLE in lbft_config.flags");
+  *bytes = sizeof(SnapshotHeader) + state_bytes(s);
+  return LBFT_OK;
+}
+
+int lbft_snapshot_save(lbft_sim* s, void* buf, size_t cap) {
+  size_t need = 0;
+  if (int r = lbft_snapshot_size(s, &need)) return r;
+  if (!buf || cap < need) return set_error(LBFT_ERR_INVALID, "snapshot buffer too small (see lbft_snapshot_size)");
+  if (!s->started) return set_error(LBFT_ERR_STATE, "nothing to snapshot: call lbft_run_until first");
+  CUDA_TRY(cudaSetDevice(s->device));
+  SnapshotHeader h{kSnapMagic, LBFT_ABI_VERSION, s->I, s->N, s->P.L.total_words, s->P.max_clock, s->last_stop, config_digest(s)};
+  memcpy(buf, &h, sizeof h);
+  CUDA_TRY(cudaMemcpy(static_cast<char*>(buf) + sizeof h, s->d_state, state_bytes(s), cudaMemcpyDeviceToHost));
+  return LBFT_OK;
+}
+
+int lbft_snapshot_load(lbft_sim* s, const void* buf, size_t bytes) {
+  size_t need = 0;
+  if (int r = lbft_snapshot_size(s, &need)) return r;
+  if (!buf || bytes < sizeof(SnapshotHeader)) return set_error(LBFT_ERR_INVALID, "not a snapshot");
+  SnapshotHeader h;
+  memcpy(&h, buf, sizeof h);
+  if (h.magic != kSnapMagic || h.abi != LBFT_ABI_VERSION) return set_error(LBFT_ERR_INVALID, "not a snapshot of this library version");
+  if (bytes != need || h.num_instances != s->I || h.num_nodes != s->N || h.total_words != s->P.L.total_words ||
+      h.max_clock != s->P.max_clock || h.config_digest != config_digest(s))
+    return set_error(LBFT_ERR_INVALID, "the snapshot was taken from a differently configured simulator");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaMemcpy(s->d_state, static_cast<const char*>(buf) + sizeof h, state_bytes(s), cudaMemcpyHostToDevice));
+  s->started = true;   // the next lbft_run_until restores the instances from their save areas
+  s->uploaded = true;  // the seeds are not needed any more
+  s->ran = false;
+  s->downloaded = false;
+  s->last_stop = h.last_stop;
+  return LBFT_OK;
 }
 
 static int need_results(lbft_sim* s, const void* out) {

@@ -263,9 +263,16 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // REC: keep DataWriter's round-switch table (LBFT_FLAG_ROUND_SWITCHES, Params::record_rs).  A template parameter rather
 // than a run-time test so that the non-recording instantiations carry no trace of it (the run-time test measured
 // +0.8..2.0 % on the generic kernels, profiles/README.md).
-template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false>
+// RES: resumable run (LBFT_FLAG_RESUMABLE): the loop stops at P.stop_clock the way loop_until(max_clock) does
+// (simulator.rs:383-391: the first event beyond it is popped and dropped), the instance registers are saved to /
+// restored from the save area, and finalize() leaves the queue alone.
+template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false>
 struct Core {
-  static_assert(!(FIXED && REC), "the compile-time layout has no round-switch table");
+  static_assert(!(FIXED && (REC || RES)), "the compile-time layout has neither a round-switch table nor a save area");
+  // Duplicate timers are accounted at push time instead of being queued (push_timer) only when every pop does not
+  // matter individually: not while recording (each pop is a sampling point) and not in resumable runs (the event
+  // dropped at a stop must be the one the reference drops).
+  static constexpr bool ELIDE = !(REC || RES);
   static constexpr int S = Mem::STRIDE;
   const Params& P;
   const Layout L;
@@ -1007,7 +1014,7 @@ struct Core {
   LBFT_HD void push_timer(uint32_t n, NodeRegs& d, int32_t t) {
     // (not while recording round switches: every pop is a DataWriter sampling point, data_writer.rs:34-50, so the
     // duplicate has to be popped where the reference pops it)
-    if (!REC && (uint32_t)t == d.f[F_LAST_TIMER]) {
+    if (ELIDE && (uint32_t)t == d.f[F_LAST_TIMER]) {
       // An UpdateTimerEvent for (n, t) is already pending with a smaller stamp.  The duplicate could
       // only ever be popped right after it (same time) and be cancelled by
       // ignore_scheduled_updates_until (simulator.rs:403-410) with no side effect: account for it
@@ -1082,7 +1089,9 @@ struct Core {
       int32_t t;
       uint32_t kind, data;
       pop_event(t, kind, data);
-      if (t > P.max_clock) break;  // unreachable: such events are dropped at push
+      // one-shot runs: unreachable, such events are dropped at push.  Resumable runs: loop_until's own exit,
+      // simulator.rs:389-391 — the popped event is gone.
+      if (t > (RES ? P.stop_clock : P.max_clock)) break;
       // DataWriter::update_round_number (data_writer.rs:34-50), called at simulator.rs:393-394 with the popped event's
       // own scheduled time.  Only the node that handled the previous event can have a larger active round than at
       // the previous pop, so at most one switch is pending.
@@ -1195,8 +1204,49 @@ struct Core {
   // ------------------------------------------------------------------------------------------
   // read-out: commit counts, last committed round and state key per node; counters; status
   // ------------------------------------------------------------------------------------------
+  // ------------------------------------------------------------------------------------------
+  // Resumable runs: the per-instance registers (and, QMODE 2, the shared-memory queue) between two launches
+  // ------------------------------------------------------------------------------------------
+  LBFT_HD void save_regs() {
+    const uint32_t b = res_area_base(L, REC);
+    uint32_t w = b;
+    const uint64_t sx[4] = {s0, s1, s2, s3};
+    for (int i = 0; i < 4; i++) { m.st(w++, (uint32_t)sx[i]); m.st(w++, (uint32_t)(sx[i] >> 32)); }
+    const uint32_t r[] = {draws, stamp, qsize, status, (uint32_t)clock, pay_free, pay_next, proc0, proc1, proc2, proc3, cancelled,
+                          max_queue, sched_notify, dedup, win, cal_t, cal_free, cal_next, REC ? rs_pend : 0u, cc0, cc1, cc2, cc3};
+    static_assert(8 + sizeof(r) / 4 <= RES_REG_WORDS, "save area too small");
+    for (uint32_t i = 0; i < sizeof(r) / 4; i++) m.st(w++, r[i]);
+    if (QMODE == 2) {
+      const uint32_t q = b + RES_REG_WORDS + L.round_cap, qd = q + L.queue_cap;
+      for (uint32_t j = 0; j < qsize; j++) m.st(q + j, sk[j * 32]);
+      for (uint32_t j = 0; j < qsize; j += 2) m.st(qd + (j >> 1), (uint32_t)sd[j * 32] | (j + 1 < qsize ? (uint32_t)sd[(j + 1) * 32] << 16 : 0u));
+    }
+  }
+  LBFT_HD void restore_regs() {
+    const uint32_t b = res_area_base(L, REC);
+    uint32_t w = b;
+    uint64_t sx[4];
+    for (int i = 0; i < 4; i++) { uint64_t lo = m.ld(w++); uint64_t hi = m.ld(w++); sx[i] = lo | (hi << 32); }
+    s0 = sx[0]; s1 = sx[1]; s2 = sx[2]; s3 = sx[3];
+    draws = m.ld(w++); stamp = m.ld(w++); qsize = m.ld(w++); status = m.ld(w++); clock = (int32_t)m.ld(w++);
+    pay_free = m.ld(w++); pay_next = m.ld(w++); proc0 = m.ld(w++); proc1 = m.ld(w++); proc2 = m.ld(w++); proc3 = m.ld(w++);
+    cancelled = m.ld(w++); max_queue = m.ld(w++); sched_notify = m.ld(w++); dedup = m.ld(w++); win = m.ld(w++);
+    cal_t = m.ld(w++); cal_free = m.ld(w++); cal_next = m.ld(w++);
+    const uint32_t rp = m.ld(w++);
+    if (REC) rs_pend = rp;
+    cc0 = m.ld(w++); cc1 = m.ld(w++); cc2 = m.ld(w++); cc3 = m.ld(w++);
+    if (QMODE == 2) {
+      const uint32_t q = b + RES_REG_WORDS + L.round_cap, qd = q + L.queue_cap;
+      for (uint32_t j = 0; j < qsize; j++) {
+        sk[j * 32] = m.ld(q + j);
+        sd[j * 32] = (uint16_t)(m.ld(qd + (j >> 1)) >> ((j & 1) * 16));
+      }
+    }
+  }
+
   LBFT_HD void finalize(uint32_t inst) {
     const uint32_t N = L.num_nodes;
+    const uint32_t scratch = RES ? res_area_base(L, REC) + RES_REG_WORDS : L.heap_time;
     uint32_t max_round = 0;
     for (uint32_t n = 0; n < N; n++) {
       uint32_t b = nbase(n);
@@ -1208,11 +1258,11 @@ struct Core {
       for (uint32_t r = lc; r != 0; r = chain_prev(r)) depth++;
       if (depth != commits) status |= ST_INVARIANT;
       uint32_t i = depth;
-      for (uint32_t r = lc; r != 0 && i > 0; r = chain_prev(r)) m.st(L.heap_time + (--i), r);
+      for (uint32_t r = lc; r != 0 && i > 0; r = chain_prev(r)) m.st(scratch + (--i), r);
       SipWords h;
       h.write_u64(depth);
       for (uint32_t k = 0; k < depth; k++) {
-        uint32_t r = m.ld(L.heap_time + k);
+        uint32_t r = m.ld(scratch + k);
         uint32_t c0 = m.ld(L.chain_base + 2 * r);
         int32_t tm = (int32_t)m.ld(L.chain_base + 2 * r + 1);
         h.write_u64(P.leader[r]);

@@ -77,8 +77,14 @@ struct Layout {
 #else
 #define LBFT_LAYOUT_FN constexpr
 #endif
+// Save area of a resumable instance: [0, RES_REG_WORDS) the per-instance registers of Core (save_regs/restore_regs);
+// then round_cap words of scratch for finalize() (the event queue is still live, so it cannot be borrowed as in a
+// one-shot run); QMODE 2 only: queue_cap key words + (queue_cap + 1) / 2 words of packed 16-bit payloads — the
+// shared-memory queue between two launches.
+constexpr uint32_t RES_REG_WORDS = 40;
+
 LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
-                          uint32_t queue_scan, uint32_t max_clock = 0, bool record_rs = false) {
+                          uint32_t queue_scan, uint32_t max_clock = 0, bool record_rs = false, bool resumable = false) {
   Layout L{};
   L.queue_scan = queue_scan;
   L.num_nodes = N;
@@ -125,11 +131,16 @@ LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue
   // with rs_table_base() — deliberately not a Layout field, so that Layout / Params keep the exact shape the
   // compile-time-layout kernel was tuned with.
   if (record_rs) o += N * (round_cap + 1);
+  // Resumable runs (LBFT_FLAG_RESUMABLE): a per-instance save area after that table, see res_area_words() below.
+  if (resumable) o += RES_REG_WORDS + round_cap + (queue_scan == 2 ? queue_cap + (queue_cap + 1) / 2 : 0);
   L.total_words = o;
   return L;
 }
 
 LBFT_LAYOUT_FN uint32_t rs_table_base(const Layout& L) { return L.pay_base + L.payload_cap * L.pay_words; }
+LBFT_LAYOUT_FN uint32_t res_area_base(const Layout& L, bool record_rs) {
+  return rs_table_base(L) + (record_rs ? L.num_nodes * (L.round_cap + 1) : 0);
+}
 
 // Everything the kernel needs that is uniform over the launch.
 struct Params {
@@ -169,6 +180,12 @@ struct Params {
   uint64_t* out_last_state;     // [I * N]
   uint32_t* out_counters;       // [I * 12] lbft_instance_counters
   uint32_t* out_status;         // [I]
+  // resumable runs (appended: nothing above moves).  The loop of this launch stops at stop_clock <= max_clock;
+  // run_flags bit 0: restore the instance from its save area instead of Simulator::new
+  int32_t stop_clock;
+  uint32_t run_flags;
+  uint32_t resumable;  // LBFT_FLAG_RESUMABLE
+  uint32_t pad2;
 };
 
 }  // namespace lbft

@@ -138,9 +138,10 @@ class BatchSimulator:
 
     def __init__(self, seeds, num_nodes, network_delay=RandomDelay(), node_config=NodeConfig(),
                  commands_per_epoch=30000, voting_rights=None, silent=None, partition_windows=0,
-                 partition_max_len=0, device=0, round_cap=0, queue_cap=0, payload_cap=0, record_round_switches=False):
+                 partition_max_len=0, device=0, round_cap=0, queue_cap=0, payload_cap=0, record_round_switches=False, resumable=False):
         self._lib = _lib.load()
         self.record_round_switches = bool(record_round_switches)  # LBFT_FLAG_ROUND_SWITCHES (DataWriter, data_writer.rs)
+        self.resumable = bool(resumable)  # LBFT_FLAG_RESUMABLE: run_until / snapshot / restore
         self.seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
         self.num_instances = int(self.seeds.shape[0])
         self.num_nodes = int(num_nodes)
@@ -170,7 +171,7 @@ class BatchSimulator:
         c.silent = None if self.silent is None else self.silent.ctypes.data
         c.partition_windows, c.partition_max_len = self.partition_windows, self.partition_max_len
         c.device, c.round_cap, c.queue_cap, c.payload_cap = self.device, self.round_cap, self.queue_cap, self.payload_cap
-        c.flags = _lib.FLAG_ROUND_SWITCHES if self.record_round_switches else 0
+        c.flags = (_lib.FLAG_ROUND_SWITCHES if self.record_round_switches else 0) | (_lib.FLAG_RESUMABLE if self.resumable else 0)
         return c
 
     def create(self, max_clock):
@@ -215,6 +216,28 @@ class BatchSimulator:
         if csv_path is not None:
             self.write_data_files(csv_path, 0)
         return BatchResult(self)
+
+    def run_until(self, stop_clock, strict=True):
+        """``lbft_run_until``: ``loop_until(GlobalTime(stop_clock), ..)`` on every instance of a resumable handle created
+        with the final horizon (``create(horizon)``); the first call is ``Simulator::new`` + ``loop_until``, later calls
+        continue — and, like the reference, each call drops the first event beyond its clock (simulator.rs:383-391)."""
+        code = self._lib.lbft_run_until(self._handle, int(stop_clock))
+        _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
+        self._read_timing()
+        return BatchResult(self)
+
+    def snapshot(self):
+        """``lbft_snapshot_save``: the whole batch between two ``run_until`` calls, as a ``numpy.uint8`` array."""
+        n = ctypes.c_size_t(0)
+        _lib.check(self._lib.lbft_snapshot_size(self._handle, ctypes.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        _lib.check(self._lib.lbft_snapshot_save(self._handle, ctypes.c_void_p(buf.ctypes.data), n.value))
+        return buf
+
+    def restore(self, snapshot):
+        """``lbft_snapshot_load`` into a handle created from the same configuration; continue with ``run_until``."""
+        buf = np.ascontiguousarray(snapshot, dtype=np.uint8)
+        _lib.check(self._lib.lbft_snapshot_load(self._handle, ctypes.c_void_p(buf.ctypes.data), buf.nbytes))
 
     def set_seeds(self, seeds):
         """Re-seed the batch: the next run is a fresh ``Simulator::new(seed, ..)`` per instance."""
@@ -329,8 +352,14 @@ class Simulator:
     ``(NodeConfig, commands_per_epoch)`` describing what the reference's closure would build.
     """
 
-    def __init__(self, rng_seed, num_nodes, network_delay, context_factory=None, **kw):
+    def __init__(self, rng_seed, num_nodes, network_delay, context_factory=None, horizon=None, **kw):
         node_config, cpe = NodeConfig(), 30000
+        # horizon: the largest clock any later loop_until will be given.  The reference needs no such thing (its heap is
+        # unbounded); the device tables are sized for it.  Without it loop_until is one-shot, as before.
+        self._horizon = None if horizon is None else int(horizon)
+        self._ran = False
+        if horizon is not None:
+            kw["resumable"] = True
         if isinstance(context_factory, NodeConfig):
             node_config = context_factory
         elif isinstance(context_factory, tuple):
@@ -340,10 +369,23 @@ class Simulator:
         self._batch = BatchSimulator([rng_seed], num_nodes, network_delay, node_config, cpe, **kw)
 
     @staticmethod
-    def new(rng_seed, num_nodes, network_delay, context_factory=None, **kw):
-        return Simulator(rng_seed, num_nodes, network_delay, context_factory, **kw)
+    def new(rng_seed, num_nodes, network_delay, context_factory=None, horizon=None, **kw):
+        return Simulator(rng_seed, num_nodes, network_delay, context_factory, horizon, **kw)
 
     def loop_until(self, max_clock, csv_path=None):
-        res = self._batch.loop_until(int(max_clock), csv_path)
+        if self._horizon is None:
+            if self._ran:
+                raise RuntimeError("loop_until was already run: pass horizon=<largest clock> to Simulator.new to call it again "
+                                   "(the device tables are sized for a horizon, include/lbft.h lbft_run_until)")
+            res = self._batch.loop_until(int(max_clock), csv_path)
+        else:
+            # simulator.rs:380 called repeatedly on one Simulator.  A DataWriter lives for ONE call (:381, :470-472), the
+            # device keeps one table per run: csv_path is only supported on one-shot simulators.
+            if csv_path is not None:
+                raise ValueError("csv_path on a resumable Simulator is not supported")
+            if not self._ran:
+                self._batch.create(self._horizon)
+            res = self._batch.run_until(int(max_clock))
+        self._ran = True
         self.result = res
         return res.contexts(0)

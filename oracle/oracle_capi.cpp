@@ -49,7 +49,8 @@ static void make_partition_plan(const lbft_config* c, uint64_t seed, SimConfig& 
 
 static void run_one(const lbft_config* c, const SimConfig& base, uint32_t inst, uint32_t* commit_counts,
                     uint64_t* last_states, lbft_instance_counters* counters, uint32_t* status,
-                    std::vector<std::vector<CommitEntry>>* logs, std::vector<lbft_round_switch>* switches = nullptr) {
+                    std::vector<std::vector<CommitEntry>>* logs, std::vector<lbft_round_switch>* switches = nullptr,
+                    const std::vector<int64_t>* stops = nullptr) {
   SimConfig s = base;
   uint64_t seed = c->seeds[inst];
   make_partition_plan(c, seed, s);
@@ -65,7 +66,10 @@ static void run_one(const lbft_config* c, const SimConfig& base, uint32_t inst, 
     }
   } collect{sim, switches};
   try {
-    sim.loop_until(s.max_clock);
+    // staged: loop_until called again and again on the same Simulator (simulator.rs:380) — each call drops the first
+    // event beyond its clock (:383-391)
+    if (stops) for (int64_t t : *stops) sim.loop_until(t);
+    else sim.loop_until(s.max_clock);
     st |= LBFT_ST_DONE;
   } catch (const OracleError&) {
     st |= LBFT_ST_INVARIANT;
@@ -136,6 +140,45 @@ int lbfo_commit_log(const lbft_config* c, uint32_t instance, uint32_t node, lbft
   const auto& h = logs[node];
   if (n) *n = h.size();
   for (size_t i = 0; i < h.size() && i < cap; i++) out[i] = lbft_commit{h[i].proposer, h[i].index, h[i].time};
+  return LBFT_OK;
+}
+
+// lbfo_run_batch with loop_until called once per entry of stops[] on each instance (the reference of lbft_run_until).
+int lbfo_run_batch_staged(const lbft_config* c, uint32_t first, uint32_t count, uint32_t threads, const int64_t* stops,
+                          size_t nstops, uint32_t* commit_counts, uint64_t* last_states, lbft_instance_counters* counters,
+                          uint32_t* status) {
+  SimConfig base;
+  if (!make_cfg(c, base, g_err)) return LBFT_ERR_INVALID;
+  if ((uint64_t)first + count > c->num_instances) { g_err = "instance range out of bounds"; return LBFT_ERR_INVALID; }
+  const std::vector<int64_t> st(stops, stops + nstops);
+  if (threads == 0) threads = 1;
+  std::atomic<uint32_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      uint32_t i = next.fetch_add(1);
+      if (i >= count) break;
+      run_one(c, base, first + i, commit_counts, last_states, counters, status, nullptr, nullptr, &st);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (uint32_t t = 1; t < threads; t++) pool.emplace_back(worker);
+  worker();
+  for (auto& t : pool) t.join();
+  return LBFT_OK;
+}
+
+// Round switches of a staged run of one instance (the DataWriter of each loop_until call is fed the same way; the
+// log of a staged run is the concatenation, kept here in one table like the device does).
+int lbfo_round_switches_staged(const lbft_config* c, uint32_t instance, const int64_t* stops, size_t nstops,
+                               lbft_round_switch* out, size_t cap, size_t* n) {
+  SimConfig base;
+  if (!make_cfg(c, base, g_err)) return LBFT_ERR_INVALID;
+  if (instance >= c->num_instances) { g_err = "index out of range"; return LBFT_ERR_INVALID; }
+  const std::vector<int64_t> st(stops, stops + nstops);
+  std::vector<lbft_round_switch> sw;
+  run_one(c, base, instance, nullptr, nullptr, nullptr, nullptr, nullptr, &sw, &st);
+  if (n) *n = sw.size();
+  for (size_t i = 0; i < sw.size() && i < cap; i++) out[i] = sw[i];
   return LBFT_OK;
 }
 

@@ -12,23 +12,40 @@
 using namespace lbft;
 static thread_local std::string g_err;
 
-template <int NMAX, int QMODE, bool REC>
+template <int NMAX, int QMODE, bool REC, bool RES>
 static void run_all(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
     std::vector<uint32_t> sk(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);  // stands in for the shared-memory queue
     std::vector<uint16_t> sd(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);
-    Core<TileMem<32>, NMAX, QMODE, false, REC> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
-    core.init(P.seeds[inst]);
+    Core<TileMem<32>, NMAX, QMODE, false, REC, RES> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
+    // QMODE 2: the stand-in for the shared-memory queue is per call, like shared memory is per launch
+    if (RES && (P.run_flags & 1u)) core.restore_regs();
+    else core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);
+    if (RES) core.save_regs();
   }
 }
 
 static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
                     uint32_t* counters, uint32_t* status, uint32_t* words_per_instance, std::vector<uint32_t>& state,
-                    Params& P);
+                    Params& P, const int64_t* stops = nullptr, size_t nstops = 0);
+
+static size_t read_round_switches(const Layout& L, const std::vector<uint32_t>& state, uint32_t num_nodes, uint32_t instance,
+                                  lbft_round_switch* out, size_t cap) {
+  const uint32_t row = L.round_cap + 1, tile = instance >> 5, lane = instance & 31;
+  size_t k = 0;
+  for (uint32_t node = 0; node < num_nodes; node++)
+    for (uint32_t r = 0; r < row; r++) {
+      const uint32_t w = state[((size_t)tile * L.total_words + rs_table_base(L) + (size_t)node * row + r) * 32 + lane];
+      if (!w) continue;
+      if (k < cap) out[k] = lbft_round_switch{node, r, (int64_t)(w - 1u)};
+      k++;
+    }
+  return k;
+}
 
 extern "C" {
 const char* hostcore_last_error(void) { return g_err.c_str(); }
@@ -67,24 +84,35 @@ int hostcore_round_switches(const lbft_config* c, uint32_t instance, lbft_round_
   Params P;
   int rc = run_impl(c, cc.data(), ls.data(), lc.data(), counters.data(), status.data(), nullptr, state, P);
   if (rc != LBFT_OK) return rc;
-  const Layout& L = P.L;
-  const uint32_t row = L.round_cap + 1, tile = instance >> 5, lane = instance & 31;
-  size_t k = 0;
-  for (uint32_t node = 0; node < c->num_nodes; node++)
-    for (uint32_t r = 0; r < row; r++) {
-      const uint32_t w = state[((size_t)tile * L.total_words + rs_table_base(L) + (size_t)node * row + r) * 32 + lane];
-      if (!w) continue;
-      if (k < cap) out[k] = lbft_round_switch{node, r, (int64_t)(w - 1u)};
-      k++;
-    }
-  if (n) *n = k;
+  if (n) *n = read_round_switches(P.L, state, c->num_nodes, instance, out, cap);
+  return LBFT_OK;
+}
+// lbft_run_until called once per stop (LBFT_FLAG_RESUMABLE required); outputs describe the state at the last stop.
+int hostcore_run_staged(const lbft_config* c, const int64_t* stops, size_t nstops, uint32_t* commit_counts,
+                        uint64_t* last_states, uint32_t* lc_round, uint32_t* counters, uint32_t* status) {
+  std::vector<uint32_t> state;
+  Params P;
+  return run_impl(c, commit_counts, last_states, lc_round, counters, status, nullptr, state, P, stops, nstops);
+}
+
+int hostcore_round_switches_staged(const lbft_config* c, uint32_t instance, const int64_t* stops, size_t nstops,
+                                   lbft_round_switch* out, size_t cap, size_t* n) {
+  if (!(c->flags & LBFT_FLAG_ROUND_SWITCHES)) { g_err = "LBFT_FLAG_ROUND_SWITCHES not set"; return LBFT_ERR_STATE; }
+  if (instance >= c->num_instances) { g_err = "instance out of range"; return LBFT_ERR_INVALID; }
+  const size_t IN = (size_t)c->num_instances * c->num_nodes;
+  std::vector<uint32_t> cc(IN), lc(IN), counters((size_t)c->num_instances * 12), status(c->num_instances), state;
+  std::vector<uint64_t> ls(IN);
+  Params P;
+  int rc = run_impl(c, cc.data(), ls.data(), lc.data(), counters.data(), status.data(), nullptr, state, P, stops, nstops);
+  if (rc != LBFT_OK) return rc;
+  if (n) *n = read_round_switches(P.L, state, c->num_nodes, instance, out, cap);
   return LBFT_OK;
 }
 }  // extern "C"
 
 static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
                     uint32_t* counters, uint32_t* status, uint32_t* words_per_instance, std::vector<uint32_t>& state,
-                    Params& P) {
+                    Params& P, const int64_t* stops, size_t nstops) {
   HostSetup hs;
   if (!hs.build(*c)) { g_err = hs.error; return LBFT_ERR_INVALID; }
   P = hs.params;
@@ -105,7 +133,19 @@ static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* las
   P.out_counters = counters;
   P.out_status = status;
   if (words_per_instance) *words_per_instance = P.L.total_words;
-#define RUN(NMAX, QS) (P.record_rs ? run_all<NMAX, QS, true>(P, state, P.zig_x, P.zig_f) : run_all<NMAX, QS, false>(P, state, P.zig_x, P.zig_f))
+  if (stops && !P.resumable) { g_err = "LBFT_FLAG_RESUMABLE not set"; return LBFT_ERR_STATE; }
+  const int64_t one_stop[1] = {P.max_clock};
+  if (!stops) { stops = one_stop; nstops = 1; }
+  // one launch per stop over the same state, like lbft_run_until
+  for (size_t stage = 0; stage < nstops; stage++) {
+    if (stops[stage] < 0 || stops[stage] > P.max_clock) { g_err = "stop_clock out of range"; return LBFT_ERR_INVALID; }
+    P.stop_clock = (int32_t)stops[stage];
+    P.run_flags = stage > 0 ? 1u : 0u;
+#define RUN(NMAX, QS)                                                                                             \
+  (P.resumable ? (P.record_rs ? run_all<NMAX, QS, true, true>(P, state, P.zig_x, P.zig_f)                           \
+                              : run_all<NMAX, QS, false, true>(P, state, P.zig_x, P.zig_f))                          \
+               : (P.record_rs ? run_all<NMAX, QS, true, false>(P, state, P.zig_x, P.zig_f)                          \
+                              : run_all<NMAX, QS, false, false>(P, state, P.zig_x, P.zig_f)))
   if (P.L.queue_scan == 2) RUN(16, 2);
   else if (P.L.queue_scan == 1) RUN(16, 1);
   else if (P.L.queue_scan == 3) {
@@ -116,5 +156,6 @@ static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* las
   else if (c->num_nodes <= 32) RUN(32, 0);
   else RUN(64, 0);
 #undef RUN
+  }
   return LBFT_OK;
 }

@@ -54,6 +54,7 @@ class LbftRoundSwitch(ctypes.Structure):
 
 
 FLAG_ROUND_SWITCHES = 1
+FLAG_RESUMABLE = 2
 
 
 def _round_switches(fn, err, seeds, num_nodes, instance, max_clock, **kw):
@@ -119,6 +120,28 @@ class Oracle:
                        ctypes.POINTER(ctypes.c_size_t)]
         return _round_switches(fn, self.lib.lbfo_last_error, seeds, num_nodes, instance, max_clock, **kw)
 
+    def run_staged(self, seeds, num_nodes, stops, max_clock=1000, threads=0, **kw):
+        """loop_until called once per stop on the same simulators (simulator.rs:380); max_clock is only the horizon
+        the device side is configured with (the oracle itself needs none)."""
+        cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
+        res = Result(cfg.num_instances, num_nodes)
+        st = np.asarray(stops, dtype=np.int64)
+        fn = self.lib.lbfo_run_batch_staged
+        fn.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, P, ctypes.c_size_t, P, P, P, P]
+        rc = fn(ctypes.byref(cfg), 0, cfg.num_instances, threads or (os.cpu_count() or 1), P(st.ctypes.data), len(st),
+                P(res.commit_counts.ctypes.data), P(res.last_states.ctypes.data), P(res.counters.ctypes.data), P(res.status.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(self.lib.lbfo_last_error().decode())
+        return res
+
+    def round_switches_staged(self, seeds, num_nodes, instance, stops, max_clock=1000, **kw):
+        st = np.asarray(stops, dtype=np.int64)
+        fn = self.lib.lbfo_round_switches_staged
+        fn.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, P, ctypes.c_size_t, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t,
+                       ctypes.POINTER(ctypes.c_size_t)]
+        return _round_switches(lambda c, i, out, cap, n: fn(c, i, P(st.ctypes.data), len(st), out, cap, n), self.lib.lbfo_last_error,
+                               seeds, num_nodes, instance, max_clock, **kw)
+
     def commit_log(self, seeds, num_nodes, instance, node, max_clock=1000, **kw):
         cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
         n = ctypes.c_size_t()
@@ -175,6 +198,30 @@ class HostCore:
         fn.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t,
                        ctypes.POINTER(ctypes.c_size_t)]
         return _round_switches(fn, self.lib.hostcore_last_error, seeds, num_nodes, instance, max_clock, **kw)
+
+    def run_staged(self, seeds, num_nodes, stops, max_clock=1000, **kw):
+        """One launch per stop over the same state (what lbft_run_until does); needs flags with FLAG_RESUMABLE."""
+        kw.setdefault("flags", FLAG_RESUMABLE)
+        cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
+        res = Result(cfg.num_instances, num_nodes)
+        res.lc_round = np.zeros((cfg.num_instances, num_nodes), np.uint32)
+        st = np.asarray(stops, dtype=np.int64)
+        fn = self.lib.hostcore_run_staged
+        fn.argtypes = [ctypes.POINTER(LbftConfig), P, ctypes.c_size_t, P, P, P, P, P]
+        rc = fn(ctypes.byref(cfg), P(st.ctypes.data), len(st), P(res.commit_counts.ctypes.data), P(res.last_states.ctypes.data),
+                P(res.lc_round.ctypes.data), P(res.counters.ctypes.data), P(res.status.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(self.lib.hostcore_last_error().decode())
+        return res
+
+    def round_switches_staged(self, seeds, num_nodes, instance, stops, max_clock=1000, **kw):
+        kw.setdefault("flags", FLAG_RESUMABLE | FLAG_ROUND_SWITCHES)
+        st = np.asarray(stops, dtype=np.int64)
+        fn = self.lib.hostcore_round_switches_staged
+        fn.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, P, ctypes.c_size_t, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t,
+                       ctypes.POINTER(ctypes.c_size_t)]
+        return _round_switches(lambda c, i, out, cap, n: fn(c, i, P(st.ctypes.data), len(st), out, cap, n), self.lib.hostcore_last_error,
+                               seeds, num_nodes, instance, max_clock, **kw)
 
 
 def assert_same(a, b, what=""):

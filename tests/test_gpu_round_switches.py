@@ -16,7 +16,9 @@ CASES = [
     (8, 1000, 40, ("lognormal", 10.0, 4.0), {}, {}),                       # calendar queue
     (9, 700, 33, ("uniform", 0, 3), dict(round_cap=256), dict(delay_kind=1, delay_lo=0, delay_hi=3, round_cap=256)),
     (40, 300, 3, ("lognormal", 10.0, 4.0), {}, {}),                        # two-word author masks
-    (4, 6000, 34, ("lognormal", 10.0, 4.0), {}, {}),                       # long horizon: binary heap
+    (4, 6000, 34, ("lognormal", 10.0, 4.0), {}, {}),                       # long horizon, small committee: HBM scan queue
+    (7, 4500, 33, ("lognormal", 10.0, 4.0), {}, {}),                       # N > 5 beyond the calendar horizon: binary heap
+    (3, 1000, 40, ("lognormal", 10.0, 4.0), dict(queue_cap=64), dict(queue_cap=64)),   # shared-memory queue while recording
 ]
 
 

@@ -13,7 +13,8 @@ from librabft_simulator_b200.simulator import format_round_switches_csv
 from tests.support import FLAG_ROUND_SWITCHES, assert_same
 
 
-# (num_nodes, max_clock, instances, extra config) — queue modes 1 (HBM scan), 3 (calendar), 0 (heap); both mask widths
+# (num_nodes, max_clock, instances, extra config) — queue modes 1 (HBM scan), 3 (calendar), 0 (heap); both mask widths.
+# (mode 2, the shared-memory queue, needs an explicit queue_cap=64 while recording: see QMODES below)
 CASES = [
     (1, 1000, 6, dict(round_cap=1056)),
     (2, 1000, 12, {}),
@@ -29,7 +30,8 @@ CASES = [
     (9, 700, 8, dict(delay_kind=1, delay_lo=0, delay_hi=3, round_cap=256)),
     (20, 600, 2, {}),
     (40, 300, 2, {}),
-    (4, 6000, 3, {}),  # long horizon: binary heap
+    (4, 6000, 3, {}),  # long horizon, small committee: still the HBM scan queue
+    (7, 4500, 2, {}),  # N > 5 beyond the calendar queue's horizon: binary heap
 ]
 
 
@@ -45,6 +47,18 @@ def test_hostcore_round_switches_match_oracle(oracle, hostcore, N, max_clock, co
         want = oracle.round_switches(seeds, N, i, max_clock, **kw)
         assert hostcore.round_switches(seeds, N, i, max_clock, **kw) == want, "instance %d" % i
         assert want, "nothing recorded"
+
+
+# the queue mode each kind of case is meant to exercise, asserted so that a comment cannot drift from the selection logic
+QMODES = [(3, 1000, dict(queue_cap=64), 2), (4, 1000, {}, 1), (4, 6000, {}, 1), (8, 1000, {}, 3), (7, 4500, {}, 0)]
+
+
+@pytest.mark.parametrize("N,max_clock,kw,qmode", QMODES)
+def test_queue_mode_coverage(oracle, hostcore, N, max_clock, kw, qmode):
+    assert hostcore.setup_info(N, max_clock, flags=FLAG_ROUND_SWITCHES, **kw)["queue_scan"] == qmode
+    seeds = [811, 812, 813]
+    for i in range(len(seeds)):
+        assert hostcore.round_switches(seeds, N, i, max_clock, **kw) == oracle.round_switches(seeds, N, i, max_clock, **kw)
 
 
 @pytest.mark.parametrize("seed,N", [(52, 3), (48, 8)])  # the reference's golden runs (simulated_run.rs:46-93)
@@ -66,7 +80,7 @@ def test_oracle_round_switch_shape(oracle, seed, N):
 
 def test_unknown_flag_bits_are_rejected(hostcore):
     with pytest.raises(RuntimeError, match="flags"):
-        hostcore.setup_info(4, flags=2)
+        hostcore.setup_info(4, flags=8)
     with pytest.raises(RuntimeError, match="LBFT_FLAG_ROUND_SWITCHES"):
         hostcore.round_switches([1], 4, 0, flags=0)
 

@@ -22,9 +22,9 @@ def kernels(path):
     return res
 
 
-def key(name):  # <NMAX, QMODE, FIXED, REC> with REC defaulting to 0 for builds that predate it
-    m = re.search(r"kernelILi(\d+)ELi(\d)ELb([01])E(?:Lb([01])E)?", name)
-    return None if not m else (int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4) or 0))
+def key(name):  # <NMAX, QMODE, FIXED, REC, RES>; REC / RES default to 0 for builds that predate them
+    m = re.search(r"kernelILi(\d+)ELi(\d)ELb([01])E(?:Lb([01])E)?(?:Lb([01])E)?", name)
+    return None if not m else (int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4) or 0), int(m.group(5) or 0))
 
 
 old = {key(k): v for k, v in kernels(sys.argv[1]).items() if key(k)}
@@ -34,4 +34,4 @@ for k in sorted(new):
         verdict = "new instantiation"
     else:
         verdict = "IDENTICAL" if old[k] == new[k] else "differs (%d -> %d instructions)" % (len(old[k]), len(new[k]))
-    print("<%d,%d,%d,%d> %6d instructions  %s" % (k + (len(new[k]), verdict)))
+    print("<%d,%d,%d,%d,%d> %6d instructions  %s" % (k + (len(new[k]), verdict)))
