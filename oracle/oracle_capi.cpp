@@ -167,6 +167,21 @@ int lbfo_run_batch_staged(const lbft_config* c, uint32_t first, uint32_t count, 
   return LBFT_OK;
 }
 
+// committed_history() of one node after a staged run.
+int lbfo_commit_log_staged(const lbft_config* c, uint32_t instance, uint32_t node, const int64_t* stops, size_t nstops,
+                           lbft_commit* out, size_t cap, size_t* n) {
+  SimConfig base;
+  if (!make_cfg(c, base, g_err)) return LBFT_ERR_INVALID;
+  if (instance >= c->num_instances || node >= c->num_nodes) { g_err = "index out of range"; return LBFT_ERR_INVALID; }
+  const std::vector<int64_t> st(stops, stops + nstops);
+  std::vector<std::vector<CommitEntry>> logs;
+  run_one(c, base, instance, nullptr, nullptr, nullptr, nullptr, &logs, nullptr, &st);
+  const auto& h = logs[node];
+  if (n) *n = h.size();
+  for (size_t i = 0; i < h.size() && i < cap; i++) out[i] = lbft_commit{h[i].proposer, h[i].index, h[i].time};
+  return LBFT_OK;
+}
+
 // Round switches of a staged run of one instance (the DataWriter of each loop_until call is fed the same way; the
 // log of a staged run is the concatenation, kept here in one table like the device does).
 int lbfo_round_switches_staged(const lbft_config* c, uint32_t instance, const int64_t* stops, size_t nstops,

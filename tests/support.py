@@ -151,6 +151,18 @@ class Oracle:
             raise RuntimeError(self.lib.lbfo_last_error().decode())
         return [(int(buf[i].proposer), int(buf[i].index), int(buf[i].time)) for i in range(n.value)]
 
+    def commit_log_staged(self, seeds, num_nodes, instance, node, stops, max_clock=1000, **kw):
+        cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
+        st = np.asarray(stops, dtype=np.int64)
+        n = ctypes.c_size_t()
+        buf = (LbftCommit * 65536)()
+        fn = self.lib.lbfo_commit_log_staged
+        fn.argtypes = [ctypes.POINTER(LbftConfig), ctypes.c_uint32, ctypes.c_uint32, P, ctypes.c_size_t, ctypes.POINTER(LbftCommit),
+                       ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        if fn(ctypes.byref(cfg), instance, node, P(st.ctypes.data), len(st), buf, 65536, ctypes.byref(n)) != 0:
+            raise RuntimeError(self.lib.lbfo_last_error().decode())
+        return [(int(buf[i].proposer), int(buf[i].index), int(buf[i].time)) for i in range(n.value)]
+
     def state_key(self, log):
         buf = (LbftCommit * max(1, len(log)))()
         for i, (p, idx, t) in enumerate(log):
