@@ -29,5 +29,22 @@ def random_config(rng):
     return n, max_clock, seed0, kw
 
 
+def random_modes(rng, max_clock):
+    """A random combination of the opt-in modes: (flags, stops).  flags: 1 record round switches, 2 resumable; stops is
+    None for a one-shot run, else the clocks of successive loop_until calls (now and then repeated or decreasing,
+    sometimes ending before the horizon)."""
+    flags = int(rng.choice([1, 2, 2, 3, 3]))
+    if not flags & 2:
+        return flags, None
+    k = int(rng.integers(2, 6))
+    stops = sorted(int(x) for x in rng.integers(0, max_clock + 1, size=k))
+    if rng.random() < 0.3:
+        i = int(rng.integers(1, k))
+        stops[i] = max(0, stops[i - 1] - int(rng.integers(0, 3)))   # repeated / slightly smaller clock
+    if rng.random() < 0.7:
+        stops[-1] = max_clock
+    return flags, stops
+
+
 BIG_CAPS = {"round_cap": 1024, "queue_cap": 8192, "payload_cap": 2048}
 CAPACITY_BITS = 2 | 4 | 8 | 128

@@ -19,14 +19,20 @@ class GpuResult:
         self.counters, self.status = res.counters, res.status
 
 
-def gpu_run(seeds, nodes, max_clock=1000, strict=True, **kw):
+def make_sim(seeds, nodes, **kw):
+    """A BatchSimulator from the keyword form of an lbft_config used by tests.support / tests.fuzz_configs."""
     from librabft_simulator_b200 import BatchSimulator, NodeConfig, RandomDelay
+    kw = dict(kw)
     delay = RandomDelay.new(kw.pop("delay_mean", 10.0), kw.pop("delay_variance", 4.0))
     if "delay_lo" in kw:
         delay = RandomDelay.uniform(kw.pop("delay_lo"), kw.pop("delay_hi"))
         kw.pop("delay_kind", None)
     nc = NodeConfig(kw.pop("target_commit_interval", 100000), kw.pop("delta", 20), kw.pop("gamma", 2.0), kw.pop("lambda_", 0.5))
-    sim = BatchSimulator(seeds, nodes, delay, nc, kw.pop("commands_per_epoch", 30000), **kw)
+    return BatchSimulator(seeds, nodes, delay, nc, kw.pop("commands_per_epoch", 30000), **kw)
+
+
+def gpu_run(seeds, nodes, max_clock=1000, strict=True, **kw):
+    sim = make_sim(seeds, nodes, **kw)
     res = sim.loop_until(max_clock, strict=strict)
     return sim, GpuResult(res)
 
