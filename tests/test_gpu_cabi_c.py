@@ -8,19 +8,20 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build_c_caller(tmp_path):
+def build_c_caller(tmp_path, name="golden_run"):
     from librabft_simulator_b200 import _build
     _build.build_product()
-    exe = str(tmp_path / "golden_run")
+    exe = str(tmp_path / name)
     libdir = os.path.dirname(_build.LIB_PATH)
-    subprocess.run(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cabi", "golden_run.c"), "-I", os.path.join(ROOT, "include"),
-                    "-L", libdir, "-llbft_b200", "-Wl,-rpath," + libdir], check=True)
+    subprocess.run(["gcc", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cabi", name + ".c"), "-I",
+                    os.path.join(ROOT, "include"), "-L", libdir, "-llbft_b200", "-Wl,-rpath," + libdir], check=True)
     return exe
 
 
-def test_c_caller_compiles_and_links(tmp_path):
-    # CPU box: the C program builds against include/lbft.h and links the product library
-    exe = build_c_caller(tmp_path)
+@pytest.mark.parametrize("name", ["golden_run", "staged_run"])
+def test_c_caller_compiles_and_links(tmp_path, name):
+    # CPU box: the C programs build against include/lbft.h and link the product library
+    exe = build_c_caller(tmp_path, name)
     assert os.path.exists(exe)
 
 
@@ -30,3 +31,26 @@ def test_c_caller_reproduces_goldens(tmp_path):
     p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert p.returncode == 0, p.stdout
     assert "golden runs reproduced" in p.stdout
+
+
+@pytest.mark.gpu
+def test_c_caller_staged_run_snapshot_and_round_switches(tmp_path, oracle):
+    """lbft_run_until / lbft_snapshot_* / lbft_round_switches from plain C, against the oracle's staged run."""
+    exe = build_c_caller(tmp_path, "staged_run")
+    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout
+    assert "restored handle tracks the original" in p.stdout
+    out = {}
+    switches = []
+    for line in p.stdout.splitlines():
+        key, *vals = line.split()
+        if key == "switch":
+            switches.append(tuple(int(v) for v in vals))
+        elif key in ("counts_at_500", "counts", "states", "switches", "snapshot_bytes"):
+            out[key] = [int(v) for v in vals]
+    mid, end = oracle.run_staged([52], 3, [500]), oracle.run_staged([52], 3, [500, 1000])
+    assert out["counts_at_500"] == mid.commit_counts[0].tolist()
+    assert out["counts"] == end.commit_counts[0].tolist()
+    assert out["states"] == end.last_states[0].tolist()
+    assert switches == oracle.round_switches_staged([52], 3, 0, [500, 1000]) and out["switches"] == [len(switches)]
+    assert out["snapshot_bytes"][0] > 32 * 4 * 500   # one 32-lane tile of state words
