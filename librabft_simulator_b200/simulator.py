@@ -284,6 +284,9 @@ class BatchSimulator:
 
     # -- results --------------------------------------------------------------------------------
     def _fetch(self, fn, dtype, shape):
+        if self._handle is None:
+            raise RuntimeError("the simulator has been closed (or not created): results are fetched from the handle on first "
+                               "access, so read them before close() / before leaving the `with` block")
         out = np.empty(shape, dtype=dtype)
         _lib.check(getattr(self._lib, fn)(self._handle, ctypes.c_void_p(out.ctypes.data)))
         return out

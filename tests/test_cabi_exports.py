@@ -78,3 +78,11 @@ def test_product_does_not_link_the_oracle():
     import subprocess
     syms = subprocess.run(["nm", "-D", "--defined-only", _build.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     assert "lbfo_" not in syms and "lbft_oracle" not in syms and "hostcore" not in syms
+
+
+def test_results_read_after_close_fail_clearly(lib):
+    """BatchResult fetches lazily from the handle: after close() that is a clear Python error, not a NULL handle in C."""
+    from librabft_simulator_b200 import BatchSimulator, RandomDelay
+    sim = BatchSimulator([1, 2], 4, RandomDelay.new(10.0, 4.0))
+    with pytest.raises(RuntimeError, match="closed"):
+        sim._fetch("lbft_commit_counts", np.uint32, (2, 4))

@@ -20,7 +20,7 @@ for name, n, max_clock, kw in NEW:
     with BatchSimulator(SEEDS, n, DELAY, record_round_switches=True, **kw) as sim:
         res = sim.loop_until(max_clock)
         sw = sum(len(sim.round_switches(i)) for i in (0, 31, 32, 39))
-    print("recording:", name, "ok", int(res.commit_counts.sum()), np.unique(res.status), "switches", sw)
+        print("recording:", name, "ok", int(res.commit_counts.sum()), np.unique(res.status), "switches", sw)   # results are lazy
     with BatchSimulator(SEEDS, n, DELAY, resumable=True, record_round_switches=True, **kw) as sim, \
             BatchSimulator(SEEDS, n, DELAY, resumable=True, record_round_switches=True, **kw) as twin:
         sim.create(max_clock)
@@ -32,4 +32,6 @@ for name, n, max_clock, kw in NEW:
         twin.run_until(2 * max_clock // 3)
         b = twin.run_until(max_clock)
         same = bool((a.last_committed_states == b.last_committed_states).all()) and sim.round_switches(39) == twin.round_switches(39)
-    print("resumable + recording, 3 stages + snapshot twin:", name, "ok", int(a.commit_counts.sum()), np.unique(a.status), "twin equal:", same)
+        print("resumable + recording, 3 stages + snapshot twin:", name, "ok", int(a.commit_counts.sum()), np.unique(a.status),
+              "twin equal:", same)
+        assert same
