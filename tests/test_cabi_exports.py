@@ -86,3 +86,9 @@ def test_results_read_after_close_fail_clearly(lib):
     sim = BatchSimulator([1, 2], 4, RandomDelay.new(10.0, 4.0))
     with pytest.raises(RuntimeError, match="closed"):
         sim._fetch("lbft_commit_counts", np.uint32, (2, 4))
+
+
+def test_every_export_is_placed_against_the_reference_in_integration_md():
+    """INTEGRATION.md says, for each C entry point, what it replaces in the reference (or that it is new)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert [name for name in _lib.EXPORTS if name not in doc] == []
