@@ -4,7 +4,6 @@ fixed in the oracle first; parity for them is device-core-vs-oracle plus referen
 (prefix-consistent logs, one-step commits, quorum arithmetic).  With every extension switched off the run
 must equal the reference goldens (checked in test_hostcore_parity.py).  CPU only (host-compiled device core)."""
 import numpy as np
-import pytest
 
 from tests.support import assert_same
 

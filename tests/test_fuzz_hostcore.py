@@ -4,7 +4,6 @@ stays within the automatically chosen table capacities, and on ALL instances onc
 import numpy as np
 
 from tests.fuzz_configs import BIG_CAPS, CAPACITY_BITS, random_config, random_modes
-from tests.support import assert_same
 
 
 def check(oracle, runner, n, max_clock, seed0, kw, count):

@@ -1,7 +1,6 @@
 """The oracle against every golden vector / known-answer test the reference holds for the hot path
 (SURVEY.md §8c).  CPU only."""
 import ctypes
-import struct
 
 import numpy as np
 

@@ -5,7 +5,6 @@ The reference's exit behaviour is part of the contract: each call pops the first
 (simulator.rs:383-391), so a staged run is a DIFFERENT simulation from a one-shot run — the test asserts that too.
 PARITY: the oracle's loop_until is the restatement pinned by the commit-log goldens; calling it repeatedly has no
 golden of its own in the reference (no test resumes a simulator), so staged parity is oracle-only."""
-import numpy as np
 import pytest
 
 from tests.support import FLAG_RESUMABLE, FLAG_ROUND_SWITCHES, assert_same
