@@ -92,3 +92,19 @@ def test_every_export_is_placed_against_the_reference_in_integration_md():
     """INTEGRATION.md says, for each C entry point, what it replaces in the reference (or that it is new)."""
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert [name for name in _lib.EXPORTS if name not in doc] == []
+
+
+def test_python_mirror_maps_its_options_onto_config_flags(lib):
+    """Host logic of the mirror, no device needed: record_round_switches / resumable / horizon -> lbft_config.flags."""
+    from librabft_simulator_b200 import BatchSimulator, RandomDelay, Simulator
+    delay = RandomDelay.new(10.0, 4.0)
+    want = {(False, False): 0, (True, False): _lib.FLAG_ROUND_SWITCHES, (False, True): _lib.FLAG_RESUMABLE,
+            (True, True): _lib.FLAG_ROUND_SWITCHES | _lib.FLAG_RESUMABLE}
+    for (rec, res), flags in want.items():
+        cfg = BatchSimulator([1, 2, 3], 4, delay, record_round_switches=rec, resumable=res).make_config(1000)
+        assert cfg.flags == flags and cfg.max_clock == 1000 and cfg.num_instances == 3 and cfg.struct_size == 152
+    assert Simulator.new(52, 3, delay, None)._batch.resumable is False
+    sim = Simulator.new(52, 3, delay, None, horizon=1000)
+    assert sim._batch.resumable is True and sim._batch.make_config(sim._horizon).flags == _lib.FLAG_RESUMABLE
+    with pytest.raises(ValueError, match="write_data_files"):       # csv_path names one simulator's directory
+        BatchSimulator([1, 2], 4, delay).loop_until(1000, "/nonexistent/never_created")
