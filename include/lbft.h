@@ -165,6 +165,10 @@ int lbft_commit_log(lbft_sim* sim, uint32_t instance, uint32_t node, lbft_commit
  * DataWriter::write_to_file's round_switches.txt (data_writer.rs:61-86); number_of_messages.txt is
  * processed[0] + processed[1] + processed[2] of lbft_counters. */
 int lbft_round_switches(lbft_sim* sim, uint32_t instance, lbft_round_switch* out, size_t cap, size_t* n);
+/* max over nodes of ActiveRound::active_round() per instance (simulator.rs:86-88): out[num_instances].  The same
+ * number as lbft_instance_counters.max_active_round, without copying the whole counter table — it is the unit of
+ * the throughput metric (simulated consensus rounds). */
+int lbft_active_rounds(lbft_sim* sim, uint32_t* out);
 /* Per-instance counters and status flags: out[num_instances]. */
 int lbft_counters(lbft_sim* sim, lbft_instance_counters* out);
 int lbft_status(lbft_sim* sim, uint32_t* out);

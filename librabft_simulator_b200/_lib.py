@@ -50,7 +50,7 @@ ST_ERROR_MASK = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST
 
 EXPORTS = [
     "lbft_create", "lbft_run", "lbft_upload", "lbft_run_device", "lbft_download", "lbft_commit_counts",
-    "lbft_last_states", "lbft_commit_log", "lbft_round_switches", "lbft_counters", "lbft_status", "lbft_timing_info",
+    "lbft_last_states", "lbft_commit_log", "lbft_round_switches", "lbft_active_rounds", "lbft_counters", "lbft_status", "lbft_timing_info",
     "lbft_memory_info", "lbft_run_until", "lbft_snapshot_size", "lbft_snapshot_save", "lbft_snapshot_load", "lbft_set_seeds", "lbft_device_buffer", "lbft_destroy", "lbft_last_error", "lbft_abi_version",
 ]
 
@@ -77,7 +77,7 @@ def load():
     lib.lbft_create.argtypes = [ctypes.POINTER(LbftConfig), ctypes.POINTER(P)]
     for name in ("lbft_run", "lbft_upload", "lbft_run_device", "lbft_download"):
         getattr(lib, name).argtypes = [P]
-    for name in ("lbft_commit_counts", "lbft_last_states", "lbft_counters", "lbft_status"):
+    for name in ("lbft_commit_counts", "lbft_last_states", "lbft_active_rounds", "lbft_counters", "lbft_status"):
         getattr(lib, name).argtypes = [P, P]
     lib.lbft_commit_log.argtypes = [P, c_u32, c_u32, ctypes.POINTER(LbftCommit), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.lbft_round_switches.argtypes = [P, c_u32, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]

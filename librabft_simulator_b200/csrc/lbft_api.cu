@@ -475,6 +475,12 @@ int lbft_counters(lbft_sim* s, lbft_instance_counters* out) {
   memcpy(out, s->h_counters, (size_t)s->I * 12 * sizeof(uint32_t));
   return LBFT_OK;
 }
+int lbft_active_rounds(lbft_sim* s, uint32_t* out) {
+  if (int r = need_results(s, out)) return r;
+  const uint32_t* c = s->h_counters + 6;  // lbft_instance_counters.max_active_round
+  for (size_t i = 0; i < s->I; i++) out[i] = c[i * 12];
+  return LBFT_OK;
+}
 int lbft_status(lbft_sim* s, uint32_t* out) {
   if (int r = need_results(s, out)) return r;
   memcpy(out, s->h_status, (size_t)s->I * sizeof(uint32_t));

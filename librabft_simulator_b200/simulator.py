@@ -123,7 +123,7 @@ class BatchResult:
     @property
     def active_rounds(self):
         """max over nodes of ``ActiveRound::active_round()`` per instance (simulator.rs:86-88)."""
-        return self.counters[:, 6]
+        return self._get("ar", "lbft_active_rounds", np.uint32, (self._sim.num_instances,))
 
     def commit_log(self, instance, author):
         return self._sim.commit_log(instance, author)

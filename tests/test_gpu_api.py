@@ -89,3 +89,13 @@ def test_commit_log_truncation_and_bounds():
     assert sim._lib.lbft_commit_log(sim._handle, 32, 0, buf, 5, ctypes.byref(n)) == -1   # instance out of range
     assert sim._lib.lbft_commit_log(sim._handle, 0, 3, buf, 5, ctypes.byref(n)) == -1    # node out of range
     sim.close()
+
+
+def test_active_rounds_getter_is_the_counter_column():
+    seeds = np.arange(900, 900 + 70, dtype=np.uint64)
+    sim = make(seeds).create(1000)
+    res = sim.run()
+    assert res.active_rounds.shape == (70,) and res.active_rounds.dtype == np.uint32
+    np.testing.assert_array_equal(res.active_rounds, res.counters[:, 6])
+    assert res.active_rounds.min() > 20
+    sim.close()
