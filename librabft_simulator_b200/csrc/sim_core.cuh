@@ -1091,7 +1091,12 @@ struct Core {
       pop_event(t, kind, data);
       // one-shot runs: unreachable, such events are dropped at push.  Resumable runs: loop_until's own exit,
       // simulator.rs:389-391 — the popped event is gone.
-      if (t > (RES ? P.stop_clock : P.max_clock)) break;
+      if (t > (RES ? P.stop_clock : P.max_clock)) {
+        // the dropped event owned a reference to its notification snapshot: give it back, or every stop leaks a slot
+        if (RES && kind == EV_NOTIFY && (data >> 16) != PAY_NONE)
+          pay_unref(data >> 16, m.ld(L.pay_base + (data >> 16) * L.pay_words + 2));
+        break;
+      }
       // DataWriter::update_round_number (data_writer.rs:34-50), called at simulator.rs:393-394 with the popped event's
       // own scheduled time.  Only the node that handled the previous event can have a larger active round than at
       // the previous pop, so at most one switch is pending.

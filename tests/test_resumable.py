@@ -90,3 +90,17 @@ def test_save_area_is_appended_after_everything_else(hostcore):
     assert plain["queue_scan"] == res["queue_scan"] == 2
     assert res["words"] == plain["words"] + 40 + rc + qc + (qc + 1) // 2
     assert both["words"] == res["words"] + 3 * (rc + 1)
+
+
+def test_many_stops_do_not_leak_notification_slots(oracle, hostcore):
+    """the event dropped at a stop (simulator.rs:389-391) may be a DataSyncNotifyEvent; its reference to
+    the shared notification snapshot has to be released, or every stop loses a payload slot for good (100 stops over a
+    1000 ms horizon used to end in LBFT_ST_PAYLOAD_OVERFLOW with the default 32-slot pool)."""
+    N, horizon, seeds = 4, 3000, list(range(7700, 7732))
+    stops = list(range(20, horizon + 1, 20))  # 150 stops
+    one = hostcore.run(seeds, N, horizon, flags=FLAG_RESUMABLE)
+    got = hostcore.run_staged(seeds, N, stops, horizon)
+    assert not (got.status & 0xFFFFFFFE).any(), sorted(set(got.status.tolist()))
+    assert_same(oracle.run_staged(seeds, N, stops, horizon), got, "150 stops")
+    # high-water mark of in-flight snapshots (lbft_instance_counters.max_payloads): same order as a one-shot run
+    assert got.counters[:, 10].max() <= one.counters[:, 10].max() + 4, (got.counters[:, 10].max(), one.counters[:, 10].max())
