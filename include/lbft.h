@@ -154,12 +154,29 @@ int lbft_upload(lbft_sim* sim);     /* seeds host -> device                     
 int lbft_run_device(lbft_sim* sim); /* init + event loop + read-out kernels, no host copies  */
 int lbft_download(lbft_sim* sim);   /* summaries device -> host                              */
 
+/* lbft_run split in two so that one host thread can drive several handles (one per GPU) at once and overlap its own
+ * work with the device: lbft_run_async enqueues seeds host->device, the kernel and the summaries device->host on the
+ * handle's stream and returns at once; lbft_wait blocks until they are done and reports like lbft_run
+ * (lbft_run == lbft_run_async + lbft_wait).  Host staging is double-buffered: while a run is in flight the getters keep
+ * serving the previous run's results, and lbft_set_seeds stages the next run's seeds without touching the buffer the
+ * in-flight upload reads.  Every other entry point that touches the device returns LBFT_ERR_STATE until lbft_wait. */
+int lbft_run_async(lbft_sim* sim);
+int lbft_wait(lbft_sim* sim);
+
 /* committed_history().len() per node (main.rs:47-53): out[instance * num_nodes + node]. */
 int lbft_commit_counts(lbft_sim* sim, uint32_t* out);
 /* last_committed_state() per node (simulated_context.rs:194-196): SipHash-1-3 key of the log. */
 int lbft_last_states(lbft_sim* sim, uint64_t* out);
 /* committed_history() of one node; writes min(*n, cap) rows, *n = full length. */
 int lbft_commit_log(lbft_sim* sim, uint32_t instance, uint32_t node, lbft_commit* out, size_t cap, size_t* n);
+/* committed_history() of EVERY context of the batch in one device pass and one copy (simulated_context.rs:98-100):
+ * out[instance * cap + k], k < cap, is row k of the instance's longest log, and every node's committed_history() is
+ * its first lens[instance * num_nodes + node] rows — the logs of one instance are prefixes of one chain because a
+ * commit extends the previous one by exactly one block (simulated_context.rs:172-174); the device verifies it and
+ * the call fails with LBFT_ERR_STATE if it does not hold for some instance (then read that instance with
+ * lbft_commit_log).  Rows past a log's end are zero; logs longer than cap are truncated (lens tells).  lens may be
+ * NULL. */
+int lbft_commit_logs(lbft_sim* sim, lbft_commit* out, size_t cap, uint32_t* lens);
 /* Round switches of one instance (needs LBFT_FLAG_ROUND_SWITCHES, else LBFT_ERR_STATE): node-major,
  * rounds ascending within a node; writes min(*n, cap) rows, *n = full length.  Replaces the data behind
  * DataWriter::write_to_file's round_switches.txt (data_writer.rs:61-86); number_of_messages.txt is
@@ -173,6 +190,9 @@ int lbft_active_rounds(lbft_sim* sim, uint32_t* out);
 int lbft_counters(lbft_sim* sim, lbft_instance_counters* out);
 int lbft_status(lbft_sim* sim, uint32_t* out);
 int lbft_timing_info(lbft_sim* sim, lbft_timing* out);
+/* Name of the kernel instantiation this handle launches, spelled like the symbol ncu and cuobjdump show (the host picks
+ * it from the configuration: committee size, horizon, capacities, flags); NUL-terminated, truncated to cap. */
+int lbft_kernel_info(lbft_sim* sim, char* buf, size_t cap);
 /* Bytes of device memory held by the handle, and the per-instance state footprint. */
 int lbft_memory_info(lbft_sim* sim, uint64_t* device_bytes, uint32_t* words_per_instance);
 
@@ -193,7 +213,7 @@ int lbft_snapshot_load(lbft_sim* sim, const void* buf, size_t bytes);
 
 /* Device address of a result buffer, for callers that consume results on the GPU (e.g. an NCCL
  * all-gather of per-instance commit counts): which = 0 commit counts [I][N] u32, 1 last states [I][N]
- * u64, 2 counters [I][12] u32, 3 status [I] u32.  Valid until lbft_destroy. */
+ * u64, 2 counters [I][12] u32, 3 status [I] u32, 4 active rounds [I] u32.  Valid until lbft_destroy. */
 int lbft_device_buffer(lbft_sim* sim, uint32_t which, void** device_ptr, size_t* bytes);
 
 void lbft_destroy(lbft_sim* sim);

@@ -3,5 +3,7 @@
 from .simulator import (BatchResult, BatchSimulator, Command, GlobalTime, NodeConfig, RandomDelay,  # noqa: F401
                         SimulatedContextView, Simulator, format_round_switches_csv, write_data_files)
 
-__all__ = ["BatchResult", "BatchSimulator", "Command", "GlobalTime", "NodeConfig", "RandomDelay",
+from .distributed import ShardedBatchSimulator, ShardedResult, shard_bounds  # noqa: F401,E402
+
+__all__ = ["ShardedBatchSimulator", "ShardedResult", "shard_bounds", "BatchResult", "BatchSimulator", "Command", "GlobalTime", "NodeConfig", "RandomDelay",
            "SimulatedContextView", "Simulator", "format_round_switches_csv", "write_data_files"]

@@ -61,6 +61,29 @@ def build_oracle(force=False):
     return ORACLE_PATH
 
 
+def build_oracle_native():
+    """The CPU-baseline build of the oracle (-O3 -march=native), compiled on the machine that times it (the GPU box: same
+    image, g++ present) into a host-specific file name so that a copy built for another CPU is never loaded.  Falls back
+    to the portable build if no compiler is available.  Returns (path, flags description)."""
+    import hashlib
+    import platform
+    try:
+        cpu = [ln for ln in open("/proc/cpuinfo") if ln.startswith(("model name", "flags"))][:2]
+    except OSError:
+        cpu = [platform.processor()]
+    tag = hashlib.sha1("".join(cpu).encode()).hexdigest()[:10]
+    path = os.path.join(ORACLE_DIR, "liblbft_oracle_native_%s.so" % tag)
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_capi.cpp", "oracle_selftest.cpp", "lbft_oracle.hpp")]
+    if _newer(path, srcs):
+        return path, "-O3 -march=native"
+    try:
+        _run(["make", "-B", "liblbft_oracle_native.so"], ORACLE_DIR)
+        os.replace(os.path.join(ORACLE_DIR, "liblbft_oracle_native.so"), path)
+        return path, "-O3 -march=native"
+    except Exception:
+        return build_oracle(), "-O2 (portable build: native build failed)"
+
+
 def build_hostcore(force=False):
     srcs = [os.path.join(HOSTCORE_DIR, "hostcore.cpp")] + [
         os.path.join(CSRC, f) for f in ("sim_core.cuh", "sim_params.h", "host_setup.hpp")]

@@ -49,9 +49,9 @@ ST_INVARIANT, ST_EPOCH_CHANGE, ST_DELAY_NEAR_INT, ST_TIME_OVERFLOW = 16, 32, 64,
 ST_ERROR_MASK = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST_INVARIANT | ST_EPOCH_CHANGE | ST_TIME_OVERFLOW
 
 EXPORTS = [
-    "lbft_create", "lbft_run", "lbft_upload", "lbft_run_device", "lbft_download", "lbft_commit_counts",
+    "lbft_create", "lbft_run", "lbft_run_async", "lbft_wait", "lbft_commit_logs", "lbft_upload", "lbft_run_device", "lbft_download", "lbft_commit_counts",
     "lbft_last_states", "lbft_commit_log", "lbft_round_switches", "lbft_active_rounds", "lbft_counters", "lbft_status", "lbft_timing_info",
-    "lbft_memory_info", "lbft_run_until", "lbft_snapshot_size", "lbft_snapshot_save", "lbft_snapshot_load", "lbft_set_seeds", "lbft_device_buffer", "lbft_destroy", "lbft_last_error", "lbft_abi_version",
+    "lbft_memory_info", "lbft_kernel_info", "lbft_run_until", "lbft_snapshot_size", "lbft_snapshot_save", "lbft_snapshot_load", "lbft_set_seeds", "lbft_device_buffer", "lbft_destroy", "lbft_last_error", "lbft_abi_version",
 ]
 
 _lib = None
@@ -75,11 +75,12 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     P = ctypes.c_void_p
     lib.lbft_create.argtypes = [ctypes.POINTER(LbftConfig), ctypes.POINTER(P)]
-    for name in ("lbft_run", "lbft_upload", "lbft_run_device", "lbft_download"):
+    for name in ("lbft_run", "lbft_run_async", "lbft_wait", "lbft_upload", "lbft_run_device", "lbft_download"):
         getattr(lib, name).argtypes = [P]
     for name in ("lbft_commit_counts", "lbft_last_states", "lbft_active_rounds", "lbft_counters", "lbft_status"):
         getattr(lib, name).argtypes = [P, P]
     lib.lbft_commit_log.argtypes = [P, c_u32, c_u32, ctypes.POINTER(LbftCommit), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    lib.lbft_commit_logs.argtypes = [P, P, ctypes.c_size_t, P]
     lib.lbft_round_switches.argtypes = [P, c_u32, ctypes.POINTER(LbftRoundSwitch), ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.lbft_timing_info.argtypes = [P, ctypes.POINTER(LbftTiming)]
     lib.lbft_run_until.argtypes = [P, c_i64]
@@ -87,6 +88,7 @@ def load():
     lib.lbft_snapshot_save.argtypes = [P, P, ctypes.c_size_t]
     lib.lbft_snapshot_load.argtypes = [P, P, ctypes.c_size_t]
     lib.lbft_memory_info.argtypes = [P, ctypes.POINTER(c_u64), ctypes.POINTER(c_u32)]
+    lib.lbft_kernel_info.argtypes = [P, ctypes.c_char_p, ctypes.c_size_t]
     lib.lbft_set_seeds.argtypes = [P, P]
     lib.lbft_device_buffer.argtypes = [P, c_u32, ctypes.POINTER(P), ctypes.POINTER(ctypes.c_size_t)]
     lib.lbft_destroy.argtypes = [P]

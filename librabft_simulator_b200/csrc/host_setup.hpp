@@ -80,6 +80,7 @@ struct HostSetup {
   std::vector<uint32_t> weights;
   std::vector<double> delay_thr;  // see build_delay_table()
   std::string error;
+  uint32_t tile_stride = 32;  // instances per state tile (lane interleaving); 1 for the warp-per-instance kernel
 
   bool build(const lbft_config& c) {
     if (c.struct_size != sizeof(lbft_config)) return fail("lbft_config.struct_size does not match this library (ABI mismatch)");

@@ -56,7 +56,8 @@ enum : uint32_t {
   ST_EPOCH_CHANGE = 1u << 5,
   ST_DELAY_NEAR_INT = 1u << 6,
   ST_TIME_OVERFLOW = 1u << 7,
-  ST_FATAL = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST_TIME_OVERFLOW
+  ST_FATAL = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST_TIME_OVERFLOW,
+  ST_ERROR_BITS = ST_FATAL | ST_INVARIANT | ST_EPOCH_CHANGE  // == LBFT_ST_ERROR_MASK (static_asserted in lbft_api.cu)
 };
 
 constexpr int32_t NODE_TIME_NEVER = 0x7fffffff;
@@ -1283,6 +1284,14 @@ struct Core {
     c[4] = cancelled; c[5] = stamp; c[6] = max_round; c[7] = draws; c[8] = max_queue;
     c[9] = sched_notify; c[10] = pay_next; c[11] = dedup;
     P.out_status[inst] = status;
+    if (P.out_rounds) P.out_rounds[inst] = max_round;
+    if (P.out_error && (status & ST_ERROR_BITS)) {
+#if defined(__CUDA_ARCH__)
+      atomicOr(P.out_error, status);
+#else
+      *P.out_error |= status;
+#endif
+    }
   }
 };
 

@@ -186,6 +186,10 @@ struct Params {
   uint32_t run_flags;
   uint32_t resumable;  // LBFT_FLAG_RESUMABLE
   uint32_t pad2;
+  // appended in round 2 (nothing above moves); either may be null (host harness)
+  uint32_t* out_rounds;  // [I] max over nodes of the pacemaker's active round = counters[6] (the unit of the throughput metric)
+  uint32_t* out_error;   // [1] OR of the status words of every instance that ended with an error bit: the host looks at one
+                         //     word instead of scanning I statuses
 };
 
 }  // namespace lbft

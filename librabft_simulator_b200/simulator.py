@@ -21,6 +21,8 @@ import numpy as np
 from . import _lib
 
 DELAY_LOGNORMAL, DELAY_UNIFORM = 0, 1
+# one row of committed_history(): include/lbft.h lbft_commit
+COMMIT_DTYPE = np.dtype([("proposer", np.uint32), ("index", np.uint32), ("time", np.int64)])
 
 
 @dataclass(frozen=True)
@@ -86,47 +88,52 @@ class SimulatedContextView:
 
 class BatchResult:
     """Results of ``BatchSimulator.loop_until``: what the reference's callers read from ``Vec<&Context>``.
-    The arrays are copied out of the library's (pinned) result buffers on first access."""
+
+    The summary arrays (commit counts, state keys, status, rounds) are copied out of the library's pinned result
+    buffers when the result is created, so a ``BatchResult`` keeps describing ITS run after the handle has been
+    re-run, re-seeded or closed.  Counters and commit logs are read on demand and are only available until the
+    handle runs again (a stale read raises instead of returning another run's data)."""
 
     def __init__(self, sim):
         self._sim = sim
-        self._cache = {}
-
-    def _get(self, name, fn, dtype, shape):
-        if name not in self._cache:
-            self._cache[name] = self._sim._fetch(fn, dtype, shape)
-        return self._cache[name]
-
-    @property
-    def commit_counts(self):
-        """``committed_history().len()`` per node: [instance, node]."""
-        return self._get("cc", "lbft_commit_counts", np.uint32, (self._sim.num_instances, self._sim.num_nodes))
-
-    @property
-    def last_committed_states(self):
-        """``last_committed_state()`` per node (SipHash-1-3 key of the commit log): [instance, node]."""
-        return self._get("ls", "lbft_last_states", np.uint64, (self._sim.num_instances, self._sim.num_nodes))
+        self._generation = sim._generation
+        I, N = sim.num_instances, sim.num_nodes
+        #: ``committed_history().len()`` per node: [instance, node]
+        self.commit_counts = sim._fetch("lbft_commit_counts", np.uint32, (I, N))
+        #: ``last_committed_state()`` per node (SipHash-1-3 key of the commit log): [instance, node]
+        self.last_committed_states = sim._fetch("lbft_last_states", np.uint64, (I, N))
+        #: max over nodes of ``ActiveRound::active_round()`` per instance (simulator.rs:86-88)
+        self.active_rounds = sim._fetch("lbft_active_rounds", np.uint32, (I,))
+        self.status = sim._fetch("lbft_status", np.uint32, (I,))
+        self._counters = None
 
     @property
     def counters(self):
-        return self._get("cnt", "lbft_counters", np.uint32, (self._sim.num_instances, 12))
+        """lbft_instance_counters per instance, [instance, 12] (fetched on first use; 48 bytes per instance)."""
+        if self._counters is None:
+            self._check_current("counters")
+            self._counters = self._sim._fetch("lbft_counters", np.uint32, (self._sim.num_instances, 12))
+        return self._counters
 
-    @property
-    def status(self):
-        return self._get("st", "lbft_status", np.uint32, (self._sim.num_instances,))
+    def _check_current(self, what):
+        if self._sim._handle is None or self._generation != self._sim._generation:
+            raise RuntimeError("the %s of this result are gone: the simulator has been run again (or closed) since; read "
+                               "them before the next run" % what)
 
     # lbft_instance_counters columns
     @property
     def events_processed(self):
         return self.counters[:, 0:4].sum(axis=1)
 
-    @property
-    def active_rounds(self):
-        """max over nodes of ``ActiveRound::active_round()`` per instance (simulator.rs:86-88)."""
-        return self._get("ar", "lbft_active_rounds", np.uint32, (self._sim.num_instances,))
-
     def commit_log(self, instance, author):
+        self._check_current("commit logs")
         return self._sim.commit_log(instance, author)
+
+    def commit_logs(self, cap=None):
+        """All commit logs of the batch in one device pass (``lbft_commit_logs``): ``(rows[instance, cap], lens[instance,
+        node])``; node n's ``committed_history()`` is ``rows[instance, :lens[instance, n]]``."""
+        self._check_current("commit logs")
+        return self._sim.commit_logs(cap)
 
     def contexts(self, instance=0):
         """The ``Vec<&Context>`` that ``loop_until`` returns for one instance."""
@@ -152,6 +159,7 @@ class BatchSimulator:
         self.partition_windows, self.partition_max_len = int(partition_windows), int(partition_max_len)
         self.device, self.round_cap, self.queue_cap, self.payload_cap = int(device), int(round_cap), int(queue_cap), int(payload_cap)
         self._handle = None
+        self._generation = 0   # bumped by every run: results of an older run know they are stale
         self.timing = None
 
     # -- lifetime -------------------------------------------------------------------------------
@@ -210,6 +218,7 @@ class BatchSimulator:
                                  "and call write_data_files(path, instance)")
             self.record_round_switches = True
         self.create(int(max_clock))
+        self._generation += 1
         code = self._lib.lbft_run(self._handle)
         _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
         self._read_timing()
@@ -221,6 +230,7 @@ class BatchSimulator:
         """``lbft_run_until``: ``loop_until(GlobalTime(stop_clock), ..)`` on every instance of a resumable handle created
         with the final horizon (``create(horizon)``); the first call is ``Simulator::new`` + ``loop_until``, later calls
         continue — and, like the reference, each call drops the first event beyond its clock (simulator.rs:383-391)."""
+        self._generation += 1
         code = self._lib.lbft_run_until(self._handle, int(stop_clock))
         _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
         self._read_timing()
@@ -237,6 +247,7 @@ class BatchSimulator:
     def restore(self, snapshot):
         """``lbft_snapshot_load`` into a handle created from the same configuration; continue with ``run_until``."""
         buf = np.ascontiguousarray(snapshot, dtype=np.uint8)
+        self._generation += 1
         _lib.check(self._lib.lbft_snapshot_load(self._handle, ctypes.c_void_p(buf.ctypes.data), buf.nbytes))
 
     def set_seeds(self, seeds):
@@ -249,7 +260,21 @@ class BatchSimulator:
 
     def run(self, strict=True):
         """``lbft_run`` on the existing handle: seeds host->device, event-loop kernel, summaries device->host."""
+        self._generation += 1
         code = self._lib.lbft_run(self._handle)
+        _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
+        self._read_timing()
+        return BatchResult(self)
+
+    def run_async(self):
+        """``lbft_run_async``: enqueue upload + kernel + download on the handle's stream and return at once; the previous
+        run's ``BatchResult`` stays valid, and ``set_seeds`` may stage the next batch meanwhile.  Finish with ``wait()``."""
+        _lib.check(self._lib.lbft_run_async(self._handle))
+
+    def wait(self, strict=True):
+        """``lbft_wait``: block until the run started by ``run_async`` is done; returns its ``BatchResult``."""
+        self._generation += 1
+        code = self._lib.lbft_wait(self._handle)
         _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
         self._read_timing()
         return BatchResult(self)
@@ -264,6 +289,7 @@ class BatchSimulator:
         _lib.check(self._lib.lbft_upload(self._handle))
 
     def run_device(self):
+        self._generation += 1
         _lib.check(self._lib.lbft_run_device(self._handle))
         self._read_timing()
 
@@ -276,6 +302,12 @@ class BatchSimulator:
         t = _lib.LbftTiming()
         _lib.check(self._lib.lbft_timing_info(self._handle, ctypes.byref(t)))
         self.timing = t
+
+    def kernel_info(self):
+        """Name of the kernel instantiation the handle launches (as ncu / cuobjdump spell it)."""
+        buf = ctypes.create_string_buffer(128)
+        _lib.check(self._lib.lbft_kernel_info(self._handle, buf, 128))
+        return buf.value.decode()
 
     def memory_info(self):
         b, w = ctypes.c_uint64(), ctypes.c_uint32()
@@ -298,6 +330,17 @@ class BatchSimulator:
         buf = (_lib.LbftCommit * max(1, n.value))()
         _lib.check(self._lib.lbft_commit_log(self._handle, instance, author, buf, n.value, ctypes.byref(n)))
         return [(int(buf[i].proposer), int(buf[i].index), int(buf[i].time)) for i in range(n.value)]
+
+    def commit_logs(self, cap=None):
+        """``lbft_commit_logs``: every ``committed_history()`` of the batch with one device pass and one copy.  Returns
+        ``(rows, lens)``: ``rows[instance, k]`` (fields ``proposer``, ``index``, ``time``) is row k of the instance's longest
+        log and node n's log is ``rows[instance, :lens[instance, n]]``."""
+        lens = np.empty((self.num_instances, self.num_nodes), dtype=np.uint32)
+        if cap is None:
+            cap = max(1, int(self._fetch("lbft_commit_counts", np.uint32, (self.num_instances, self.num_nodes)).max()))
+        rows = np.empty((self.num_instances, int(cap)), dtype=COMMIT_DTYPE)
+        _lib.check(self._lib.lbft_commit_logs(self._handle, ctypes.c_void_p(rows.ctypes.data), int(cap), ctypes.c_void_p(lens.ctypes.data)))
+        return rows, lens
 
     def round_switches(self, instance):
         """``DataWriter::nodes_round_switch`` of one instance as ``[(node, round, time)]``, node-major

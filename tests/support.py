@@ -71,8 +71,12 @@ def _round_switches(fn, err, seeds, num_nodes, instance, max_clock, **kw):
 
 
 class Oracle:
-    def __init__(self):
-        path = _build.build_oracle()
+    def __init__(self, native=False):
+        """native=True: the -O3 -march=native build made on this machine (the CPU-baseline leg of bench.py)."""
+        if native:
+            path, self.build_flags = _build.build_oracle_native()
+        else:
+            path, self.build_flags = _build.build_oracle(), "-O2"
         self.lib = ctypes.CDLL(path)
         L = self.lib
         L.lbfo_last_error.restype = ctypes.c_char_p

@@ -15,18 +15,33 @@ import os, sys
 import numpy as np
 sys.path.insert(0, %(root)r)
 import torch.distributed as dist
-from librabft_simulator_b200.distributed import run_sharded, shard_bounds
+from librabft_simulator_b200.distributed import ShardedBatchSimulator
 from tests.support import HostCore
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 hc = HostCore()
+
+class HostLocal:
+    # stand-in for this rank's BatchSimulator (same create / set_seeds / run surface): the host-compiled device core
+    def __init__(self, shard): self.shard = shard
+    def create(self, max_clock): self.max_clock = max_clock; return self
+    def close(self): pass
+    def set_seeds(self, shard): self.shard = shard
+    def run(self, strict=True):
+        r = hc.run(self.shard, 4, self.max_clock)
+        r.last_committed_states, r.active_rounds = r.last_states, np.ascontiguousarray(r.counters[:, 6])
+        return r
+
 seeds = np.arange(300, 364, dtype=np.uint64)
-def run_local(s):
-    r = hc.run(s, 4, 1000)
-    return r.commit_counts, r.last_states
-counts, states = run_sharded(seeds, 4, 1000, rank, world, run_local, dist=dist)
-np.save(os.path.join(%(out)r, "counts_%%d.npy" %% rank), counts)
-np.save(os.path.join(%(out)r, "states_%%d.npy" %% rank), states)
+sim = ShardedBatchSimulator(seeds, 4, rank=rank, world=world, dist=dist, make_local=HostLocal)
+res = sim.loop_until(1000)
+assert (res.lo, res.hi) == (32 * rank, 32 * rank + 32)
+np.save(os.path.join(%(out)r, "counts_%%d.npy" %% rank), res.commit_counts)
+np.save(os.path.join(%(out)r, "states_%%d.npy" %% rank), res.last_committed_states)
+np.save(os.path.join(%(out)r, "rounds_%%d.npy" %% rank), res.active_rounds)
+sim.set_seeds(seeds + 1000)          # re-seed the whole job: every rank keeps its own contiguous shard
+res2 = sim.run()
+np.save(os.path.join(%(out)r, "counts2_%%d.npy" %% rank), res2.commit_counts)
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -62,6 +77,19 @@ def test_two_rank_gloo_matches_single_process(tmp_path, oracle):
         assert p.returncode == 0, out.decode()[-2000:]
     seeds = np.arange(300, 364, dtype=np.uint64)
     ref = oracle.run(seeds, 4, 1000)
+    ref2 = oracle.run(seeds + 1000, 4, 1000)
     for rank in range(2):
         np.testing.assert_array_equal(np.load(tmp_path / ("counts_%d.npy" % rank)), ref.commit_counts)
         np.testing.assert_array_equal(np.load(tmp_path / ("states_%d.npy" % rank)), ref.last_states)
+        np.testing.assert_array_equal(np.load(tmp_path / ("rounds_%d.npy" % rank)), ref.counters[:, 6])
+        np.testing.assert_array_equal(np.load(tmp_path / ("counts2_%d.npy" % rank)), ref2.commit_counts)
+
+
+def test_functional_form_and_uneven_batches():
+    from librabft_simulator_b200.distributed import ShardedBatchSimulator, run_sharded
+    import pytest
+    with pytest.raises(ValueError, match="multiple of the world size"):
+        ShardedBatchSimulator(np.arange(7), 4, rank=0, world=2, make_local=lambda s: None)
+    seeds = np.arange(10, 18, dtype=np.uint64)
+    counts, states = run_sharded(seeds, 3, 1000, 0, 1, lambda s: (np.tile(s[:, None], (1, 3)), np.tile(s[:, None] * 2, (1, 3))))
+    assert counts.shape == (8, 3) and (counts[:, 0] == seeds).all() and (states[:, 2] == seeds * 2).all()

@@ -99,3 +99,77 @@ def test_active_rounds_getter_is_the_counter_column():
     np.testing.assert_array_equal(res.active_rounds, res.counters[:, 6])
     assert res.active_rounds.min() > 20
     sim.close()
+
+
+def test_async_run_keeps_previous_results_readable(oracle):
+    """lbft_run_async / lbft_wait: the previous run's results live in the other set of host mirrors, the next batch's seeds
+    are staged while a run is in flight, and every device-touching call is refused until lbft_wait."""
+    from librabft_simulator_b200 import _lib
+    s0, s1 = np.arange(100, 196, dtype=np.uint64), np.arange(5100, 5196, dtype=np.uint64)
+    sim = make(s0).create(1000)
+    first = sim.run()
+    sim.set_seeds(s1)
+    sim.run_async()
+    with pytest.raises(_lib.LbftError) as e:
+        sim.run()
+    assert e.value.code == -3
+    out = np.zeros((96, 4), np.uint64)                      # read run 0 through the C getter WHILE run 1 is in flight
+    assert sim._lib.lbft_last_states(sim._handle, ctypes.c_void_p(out.ctypes.data)) == 0
+    np.testing.assert_array_equal(out, first.last_committed_states)
+    second = sim.wait()
+    np.testing.assert_array_equal(first.last_committed_states, oracle.run(s0, 4, 1000).last_states)   # eager copy: still run 0
+    np.testing.assert_array_equal(second.last_committed_states, oracle.run(s1, 4, 1000).last_states)
+    with pytest.raises(RuntimeError, match="run again"):
+        first.counters                                       # lazily fetched data of an older run is refused, not wrong
+    sim.close()
+
+
+@pytest.mark.parametrize("nodes,count,kw", [(4, 200, {}), (3, 33, {}), (7, 64, dict(partition_windows=3, partition_max_len=200)),
+                                            (4, 40, dict(silent=[0, 0, 0, 1]))])
+def test_bulk_commit_logs_match_the_per_node_reader(oracle, nodes, count, kw):
+    seeds = np.arange(3000, 3000 + count, dtype=np.uint64)
+    sim = make(seeds, nodes, **kw).create(1000)
+    res = sim.run()
+    rows, lens = res.commit_logs()
+    np.testing.assert_array_equal(lens, res.commit_counts)
+    assert rows.shape == (count, max(1, int(lens.max())))
+    for i in sorted({0, 1, count // 2, count - 1}):
+        for n in range(nodes):
+            got = [(int(r["proposer"]), int(r["index"]), int(r["time"])) for r in rows[i, :lens[i, n]]]
+            assert got == sim.commit_log(i, n) == oracle.commit_log(seeds, nodes, i, n, 1000, **kw)
+    # state key == SipHash of the returned rows, for EVERY instance and node (simulated_context.rs:51-55)
+    for i in range(count):
+        for n in range(nodes):
+            log = [(int(r["proposer"]), int(r["index"]), int(r["time"])) for r in rows[i, :lens[i, n]]]
+            assert oracle.state_key(log) == int(res.last_committed_states[i, n])
+    small, lens2 = sim.commit_logs(cap=3)                    # truncation: lens still tells the full length
+    np.testing.assert_array_equal(lens2, lens)
+    np.testing.assert_array_equal(small, rows[:, :3])
+    sim.close()
+
+
+def test_rounds_device_buffer_and_kernel_info():
+    import torch
+    seeds = np.arange(40, 104, dtype=np.uint64)
+    sim = make(seeds).create(1000)
+    res = sim.run()
+    ptr, nbytes = sim.device_buffer(4)
+    assert nbytes == 64 * 4
+
+    class Cai:
+        __cuda_array_interface__ = {"shape": (64,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    np.testing.assert_array_equal(torch.as_tensor(Cai(), device="cuda:0").cpu().numpy().astype(np.uint32), res.active_rounds)
+    assert sim.kernel_info().startswith("lbft_")
+    sim.close()
+
+
+def test_sharded_simulator_single_rank(oracle):
+    """ShardedBatchSimulator with world 1 is the plain path; (world > 1: tests/test_distributed_gloo.py on CPU, bench.py
+    under torchrun on GPUs)."""
+    from librabft_simulator_b200 import RandomDelay, ShardedBatchSimulator
+    seeds = np.arange(8000, 8064, dtype=np.uint64)
+    res = ShardedBatchSimulator(seeds, 4, RandomDelay.new(10.0, 4.0)).loop_until(1000)
+    ref = oracle.run(seeds, 4, 1000)
+    np.testing.assert_array_equal(res.commit_counts, ref.commit_counts)
+    np.testing.assert_array_equal(res.last_committed_states, ref.last_states)
+    np.testing.assert_array_equal(res.active_rounds, ref.counters[:, 6])

@@ -18,7 +18,7 @@ def build_c_caller(tmp_path, name="golden_run"):
     return exe
 
 
-@pytest.mark.parametrize("name", ["golden_run", "staged_run"])
+@pytest.mark.parametrize("name", ["golden_run", "staged_run", "multi_handle"])
 def test_c_caller_compiles_and_links(tmp_path, name):
     # CPU box: the C programs build against include/lbft.h and link the product library
     exe = build_c_caller(tmp_path, name)
@@ -54,3 +54,15 @@ def test_c_caller_staged_run_snapshot_and_round_switches(tmp_path, oracle):
     assert out["states"] == end.last_states[0].tolist()
     assert switches == oracle.round_switches_staged([52], 3, 0, [500, 1000]) and out["switches"] == [len(switches)]
     assert out["snapshot_bytes"][0] > 32 * 4 * 500   # one 32-lane tile of state words
+
+
+@pytest.mark.gpu
+def test_c_caller_drives_eight_handles_from_one_thread(tmp_path):
+    """lbft_run_async / lbft_wait: one thread, eight handles (spread over every visible GPU), double-buffered host staging;
+    lbft_commit_logs against lbft_commit_log."""
+    import torch
+    exe = build_c_caller(tmp_path, "multi_handle")
+    env = dict(os.environ, LBFT_TEST_DEVICES=str(torch.cuda.device_count()))
+    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stdout
+    assert "async handles agree with synchronous runs" in p.stdout

@@ -140,3 +140,17 @@ def test_prefix_consistency_many_seeds(oracle):
             longest = max(logs, key=len)
             for lg in logs:
                 assert lg == longest[: len(lg)]
+
+
+def test_native_build_matches_the_portable_one(oracle):
+    """The CPU-baseline leg of bench.py times the -O3 -march=native build of the oracle; it must remain the
+    same function: goldens and a seed sweep, bit for bit."""
+    from tests.support import Oracle, assert_same
+    native = Oracle(native=True)
+    r = native.run([52], 3, 1000)
+    assert r.commit_counts.tolist() == [[27, 27, 27]] and r.last_states.tolist() == [[11134312813757838303] * 3]
+    r = native.run([48], 8, 1000)
+    assert r.last_states.tolist() == [[12785928431398617538] * 7 + [4890275890002623733]]
+    seeds = np.arange(900, 1100, dtype=np.uint64)
+    for nodes, kw in ((4, {}), (7, dict(partition_windows=4, partition_max_len=150)), (4, dict(delay_kind=1, delay_lo=5, delay_hi=15))):
+        assert_same(oracle.run(seeds, nodes, 1000, **kw), native.run(seeds, nodes, 1000, **kw), "native vs portable N=%d" % nodes)
