@@ -197,7 +197,10 @@ def run_cpu_sample(cfg, seeds, threads):
 def oracle_seconds_per_instance(cfg, threads):
     """Probe: wall seconds per instance with `threads` threads busy (one instance per task)."""
     n = min(cfg["instances"], 2 * threads)
-    _, dt, _ = run_cpu_sample(cfg, step_seeds(cfg, 4000, 0, n), threads)
+    _, dt, _ = run_cpu_sample(cfg, step_seeds(cfg, 4000, 0, n), threads)   # also warms the thread pool / page cache
+    if dt < 0.2:  # too short to extrapolate from: take a sample that runs for a noticeable time
+        n = min(cfg["instances"], max(n, int(n * 0.5 / max(dt, 1e-4))))
+        _, dt, _ = run_cpu_sample(cfg, step_seeds(cfg, 4100, 0, n), threads)
     return dt / n
 
 
@@ -404,15 +407,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi needs a moment before its first sample: start it ahead of the warm-up (also load) so that the short timed
+    # region is covered
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
     # ---------------- warm-up (both legs) ----------------
     for w in range(args.warmup):
         sharded.set_seeds(job_seeds(10000 + w))
         sharded.run(strict=False)
     barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
 
     # ---------------- e2e leg: host buffers in, host results out, every step ----------------
     e2e_rounds = 0.0

@@ -16,10 +16,11 @@ ORACLE_PATH = os.path.join(ORACLE_DIR, "liblbft_oracle.so")
 HOSTCORE_DIR = os.path.join(ROOT, "tests", "hostcore")
 HOSTCORE_PATH = os.path.join(HOSTCORE_DIR, "libhostcore.so")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# Translation units of the product library: the host runtime (C ABI) and the kernel instantiations, one group per file so
+# that they compile in parallel and the bench kernel (k_fixed.cu) can be rebuilt alone.
+PRODUCT_UNITS = ["lbft_api.cu", "k_fixed.cu", "k_scan.cu", "k_calendar.cu", "k_heap.cu", "k_wide.cu"]
+PRODUCT_HEADERS = ["kernels.cuh", "sim_core.cuh", "sim_params.h", "host_setup.hpp"]
 
 
 def _newer(target, sources):
@@ -40,16 +41,28 @@ def nvcc_path():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build_product(force=False, verbose_ptxas=False):
-    srcs = [os.path.join(CSRC, f) for f in ("lbft_api.cu", "sim_core.cuh", "sim_params.h", "host_setup.hpp")]
-    srcs.append(os.path.join(ROOT, "include", "lbft.h"))
-    if not force and _newer(LIB_PATH, srcs):
-        return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-o", LIB_PATH, "lbft_api.cu"]
-    out = _run(cmd, CSRC)
+def build_product(force=False, verbose_ptxas=False, extra_flags=(), lib_path=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo on every unit (objects in csrc/build/, in parallel), then one
+    shared library.  Only units older than their sources are recompiled."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib_path = lib_path or LIB_PATH
+    headers = [os.path.join(CSRC, f) for f in PRODUCT_HEADERS] + [os.path.join(ROOT, "include", "lbft.h")]
+    objdir = os.path.join(CSRC, "build" if lib_path == LIB_PATH else "build_" + os.path.basename(lib_path))
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for unit in PRODUCT_UNITS:
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        if force or verbose_ptxas or extra_flags or not _newer(obj, headers + [os.path.join(CSRC, unit)]):
+            jobs.append((unit, obj))
+    flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose_ptxas else [])
+    with ThreadPoolExecutor(max_workers=min(len(PRODUCT_UNITS), os.cpu_count() or 2)) as pool:
+        outs = list(pool.map(lambda j: _run([nvcc_path()] + flags + ["-c", "-o", j[1], j[0]], CSRC), jobs))
     if verbose_ptxas:
-        print(out)
-    return LIB_PATH
+        print("\n".join(outs))
+    objs = [os.path.join(objdir, u.replace(".cu", ".o")) for u in PRODUCT_UNITS]
+    if jobs or not _newer(lib_path, objs):
+        _run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_path] + objs, CSRC)
+    return lib_path
 
 
 def build_oracle(force=False):

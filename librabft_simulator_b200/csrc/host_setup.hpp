@@ -81,6 +81,7 @@ struct HostSetup {
   std::vector<double> delay_thr;  // see build_delay_table()
   std::string error;
   uint32_t tile_stride = 32;  // instances per state tile (lane interleaving); 1 for the warp-per-instance kernel
+  bool use_wide = false;      // launch lbft_wide_kernel (one warp per instance) instead of one thread per instance
 
   bool build(const lbft_config& c) {
     if (c.struct_size != sizeof(lbft_config)) return fail("lbft_config.struct_size does not match this library (ABI mismatch)");
@@ -166,6 +167,18 @@ struct HostSetup {
     p.stop_clock = p.max_clock;
     p.run_flags = 0;
     p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0);
+    // One thread per instance needs tens of thousands of instances to fill a B200 (65 536 x 4 authors is exactly one wave of
+    // warps) and serialises the 32 instances of a warp through every fan-out; one WARP per instance (lbft_wide_kernel) has
+    // no cross-instance divergence and splits fan-outs, queue scans and per-author vectors over its lanes.  Measured
+    // cross-over (profiles/README.md, round 2): small committees switch at ~16 K instances, committees of 6 and more
+    // always profit.  Recording / resumable handles stay on the thread kernel (the wide one has no save area).
+    // LBFT_FORCE_KERNEL=wide|thread overrides the choice (A/B measurements).
+    use_wide = !record && (N >= 6 || c.num_instances <= 16384);
+    if (const char* f = std::getenv("LBFT_FORCE_KERNEL")) {
+      if (!strcmp(f, "wide") && !record) use_wide = true;
+      if (!strcmp(f, "thread")) use_wide = false;
+    }
+    tile_stride = use_wide ? 1u : 32u;
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
     leader.resize(rcap + 1);
     for (uint32_t r = 0; r <= rcap; r++) leader[r] = (uint8_t)pick_author(weights, total, siphash13_u64(r));

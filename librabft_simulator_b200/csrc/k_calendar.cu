@@ -1,0 +1,10 @@
+// k_calendar.cu — thread-per-instance kernels over the calendar queue (QMODE 3), committees of 6..64.
+#include "kernels.cuh"
+namespace lbft {
+cudaError_t launch_calendar(const KernelSel& k, const Params& P, cudaStream_t stream) {
+  if (k.wide || k.fixed || k.qmode != 3) return cudaErrorInvalidValue;
+  if (k.nmax == 16) return launch_thread_variants<16, 3>(k, P, stream);
+  if (k.nmax == 32) return launch_thread_variants<32, 3>(k, P, stream);
+  return launch_thread_variants<64, 3>(k, P, stream);
+}
+}  // namespace lbft

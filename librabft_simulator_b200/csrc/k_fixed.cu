@@ -1,0 +1,11 @@
+// k_fixed.cu — the bench kernel: four authors, default capacities, the reference's own delay model; layout is a compile-time
+// constant (sim_core.cuh FIXED).  BASELINE configs[2].
+#include "kernels.cuh"
+namespace lbft {
+cudaError_t launch_fixed(const KernelSel& k, const Params& P, cudaStream_t stream) {
+  if (k.wide || !k.fixed || k.qmode != 2) return cudaErrorInvalidValue;
+  constexpr int T = LaunchShape<2>::kThreads;
+  lbft_event_loop_kernel<16, 2, true><<<(P.num_instances + T - 1) / T, T, (size_t)(T / 32) * 64 * (32 * 4 + 32 * 2), stream>>>(P);
+  return cudaGetLastError();
+}
+}  // namespace lbft

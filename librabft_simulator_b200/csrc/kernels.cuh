@@ -1,0 +1,139 @@
+// kernels.cuh — the two kernel templates over sim_core.cuh and the per-translation-unit launchers.
+//
+//   lbft_event_loop_kernel<NMAX, QMODE, FIXED, REC, RES>   one THREAD per instance, 32 instances per warp tile (large batches)
+//   lbft_wide_kernel<NMAX, QMODE>                          one WARP per instance (small batches, large committees)
+//
+// Both do init -> event loop -> read-out in a single launch.  The instantiations are spread over several .cu files
+// (k_fixed.cu, k_scan.cu, k_calendar.cu, k_heap.cu, k_wide.cu) so that they compile in parallel and the bench kernel
+// can be rebuilt alone; lbft_api.cu only sees the launch_* functions declared at the end.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sim_core.cuh"
+
+namespace lbft {
+
+constexpr uint32_t kThrSmem = 256;  // doubles: delay thresholds held in shared memory when they fit
+
+// Launch shapes of the thread-per-instance kernel.  QMODE 0/1/3: one-warp blocks, 14 resident per SM (2 048 tiles of a
+// 65 536-instance batch over 148 SMs; <= 144 registers/thread keeps every tile resident).  QMODE 2: two-warp blocks, 7 per
+// SM, so that the ziggurat/threshold tables (6 KB) are shared by two tiles and the per-tile event queues (queue_cap x 32 x
+// 6 B) fit in the 227 KB of shared memory.
+template <int QMODE>
+struct LaunchShape {
+  static constexpr int kThreads = QMODE == 2 ? 64 : 32;
+  static constexpr int kBlocksPerSm = QMODE == 2 ? 7 : 14;
+};
+
+template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false>
+__global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
+  // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
+  // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
+  // measured 1.5x slower for the whole kernel (44.1 vs 28.9 ms).
+  __shared__ double s_zx[257];
+  __shared__ double s_zf[257];
+  __shared__ double s_thr[kThrSmem];  // delay thresholds (same scattered access pattern), when they fit
+  extern __shared__ uint32_t s_queue[];  // QMODE 2: per warp [queue_cap][32] u32 keys, then [queue_cap][32] u16 payload words
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) {
+    s_zx[i] = P.zig_x[i];
+    s_zf[i] = P.zig_f[i];
+  }
+  const bool thr_fits = P.delay_kmax != 0 && P.delay_kmax + 2 <= kThrSmem;
+  if (thr_fits)
+    for (uint32_t i = threadIdx.x; i < P.delay_kmax + 2; i += blockDim.x) s_thr[i] = P.delay_thr[i];
+  __syncthreads();
+  const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= P.num_instances) return;
+  const uint32_t tile = inst >> 5, lane = inst & 31;
+  TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32, lane};
+  uint32_t* sk = nullptr;
+  uint16_t* sd = nullptr;
+  if (QMODE == 2) {
+    const uint32_t warp = threadIdx.x >> 5, qcap = P.L.queue_cap;
+    uint32_t* base = s_queue + (size_t)warp * (qcap * 32 + qcap * 16);  // keys (qcap*32 words) + payload (qcap*32 halves)
+    sk = base + lane;
+    sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
+  }
+  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
+  else core.init(P.seeds[inst]);
+  core.run();
+  core.finalize(inst);
+  if (RES) core.save_regs();
+}
+
+// ---- warp per instance -----------------------------------------------------------------------------------------
+// kWideWarps warps per block, each on its own instance (instance = global warp index; the hardware block scheduler hands
+// out the next block as soon as one retires, which is the work queue SURVEY §8e asks for).  The state of an instance is one
+// contiguous extent (TileMem<1>: stride 1), tables are read through L1 (every lane reads the same element), the
+// shared-memory queue of QMODE 2 and the fan-out scratch are per warp.
+constexpr int kWideWarps = 4;
+constexpr int kWideBlocksPerSm = 4;  // 16 warps per SM: <= 128 registers per thread
+
+LBFT_LAYOUT_FN uint32_t wide_smem_words_per_warp(uint32_t queue_cap, int qmode) {
+  const uint32_t scratch = (uint32_t)((sizeof(WideScratch) + 7) / 8 * 2);
+  return scratch + (qmode == 2 ? ((queue_cap + (queue_cap + 1) / 2 + 1) & ~1u) : 0);  // even: the scratch holds doubles
+}
+
+template <int NMAX, int QMODE>
+__global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(8) uint32_t s_wide[];
+  const uint32_t warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  const uint32_t inst = blockIdx.x * kWideWarps + warp;
+  if (inst >= P.num_instances) return;  // whole warps leave together: everything below is warp-uniform
+  uint32_t* base = s_wide + (size_t)warp * wide_smem_words_per_warp(P.L.queue_cap, QMODE);
+  WideScratch* ws = reinterpret_cast<WideScratch*>(base);
+  uint32_t* sk = base + (sizeof(WideScratch) + 7) / 8 * 2;
+  uint16_t* sd = reinterpret_cast<uint16_t*>(sk + P.L.queue_cap);
+  TileMem<1> mem{P.state + (size_t)inst * P.L.total_words, 0};
+  Core<TileMem<1>, NMAX, QMODE, false, false, false, 32> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
+  core.wl = wl;
+  core.ws = ws;
+  core.init(P.seeds[inst]);
+  core.run();
+  core.finalize(inst);
+}
+
+// What the host decided to launch for a handle (host_setup.hpp / lbft_api.cu select_kernel).
+struct KernelSel {
+  bool wide;   // lbft_wide_kernel instead of lbft_event_loop_kernel
+  int nmax;    // 16 / 32 / 64: width of the author masks
+  int qmode;   // Layout::queue_scan
+  bool fixed, rec, res;
+};
+
+// One per translation unit; each returns cudaErrorInvalidValue if the selection is not one of its instantiations.
+cudaError_t launch_fixed(const KernelSel& k, const Params& P, cudaStream_t stream);
+cudaError_t launch_scan(const KernelSel& k, const Params& P, cudaStream_t stream);
+cudaError_t launch_calendar(const KernelSel& k, const Params& P, cudaStream_t stream);
+cudaError_t launch_heap(const KernelSel& k, const Params& P, cudaStream_t stream);
+cudaError_t launch_wide(const KernelSel& k, const Params& P, cudaStream_t stream);
+
+// Shared by the launchers of the thread-per-instance kernel.
+template <int NMAX, int QM>
+inline cudaError_t launch_thread_variants(const KernelSel& k, const Params& P, cudaStream_t stream) {
+  constexpr int T = LaunchShape<QM>::kThreads;
+  const uint32_t blocks = (P.num_instances + T - 1) / T;
+  const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2) : 0;
+  if (k.rec && k.res) lbft_event_loop_kernel<NMAX, QM, false, true, true><<<blocks, T, dyn, stream>>>(P);
+  else if (k.res) lbft_event_loop_kernel<NMAX, QM, false, false, true><<<blocks, T, dyn, stream>>>(P);
+  else if (k.rec) lbft_event_loop_kernel<NMAX, QM, false, true><<<blocks, T, dyn, stream>>>(P);
+  else lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, stream>>>(P);
+  return cudaGetLastError();
+}
+
+template <int NMAX, int QM>
+inline cudaError_t launch_wide_variant(const Params& P, cudaStream_t stream) {
+  const uint32_t blocks = (P.num_instances + kWideWarps - 1) / kWideWarps;
+  const size_t dyn = (size_t)kWideWarps * wide_smem_words_per_warp(P.L.queue_cap, QM) * sizeof(uint32_t);
+  static bool attr_done = false;  // (one attribute per instantiation; harmless if two threads race)
+  if (!attr_done && dyn > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(lbft_wide_kernel<NMAX, QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  lbft_wide_kernel<NMAX, QM><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace lbft

@@ -16,7 +16,7 @@
 
 #include "../../include/lbft.h"
 #include "host_setup.hpp"
-#include "sim_core.cuh"
+#include "kernels.cuh"
 
 using namespace lbft;
 
@@ -27,59 +27,6 @@ static_assert(LBFT_SAME(ST_DONE, LBFT_ST_DONE) && LBFT_SAME(ST_ROUND_OVERFLOW, L
                   LBFT_SAME(ST_DELAY_NEAR_INT, LBFT_ST_DELAY_NEAR_INT) && LBFT_SAME(ST_TIME_OVERFLOW, LBFT_ST_TIME_OVERFLOW),
               "status bits out of sync with include/lbft.h");
 static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter layout");
-
-// ---------------------------------------------------------------------------------------------
-// Kernel: one thread per simulator instance, one warp per 32-instance tile; init -> event loop -> read-out in a
-// single launch.  Small blocks so that the 2 048 tiles of a 65 536-instance batch spread evenly over 148 SMs.
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t kThrSmem = 256;  // doubles: delay thresholds held in shared memory when they fit
-
-// Launch shapes.  QMODE 0/1: one-warp blocks, 14 resident per SM (2 048 tiles of a 65 536-instance batch over 148
-// SMs; <= 144 registers/thread keeps every tile resident).  QMODE 2: two-warp blocks, 7 per SM, so that the
-// ziggurat/threshold tables (6 KB) are shared by two tiles and the per-tile event queues (queue_cap x 32 x 6 B)
-// fit in the 227 KB of shared memory.
-template <int QMODE>
-struct LaunchShape {
-  static constexpr int kThreads = QMODE == 2 ? 64 : 32;
-  static constexpr int kBlocksPerSm = QMODE == 2 ? 7 : 14;
-};
-
-template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false>
-__global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
-  // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
-  // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
-  // measured 1.5x slower for the whole kernel (44.1 vs 28.9 ms).
-  __shared__ double s_zx[257];
-  __shared__ double s_zf[257];
-  __shared__ double s_thr[kThrSmem];  // delay thresholds (same scattered access pattern), when they fit
-  extern __shared__ uint32_t s_queue[];  // QMODE 2: per warp [queue_cap][32] u32 keys, then [queue_cap][32] u16 payload words
-  for (int i = threadIdx.x; i < 257; i += blockDim.x) {
-    s_zx[i] = P.zig_x[i];
-    s_zf[i] = P.zig_f[i];
-  }
-  const bool thr_fits = P.delay_kmax != 0 && P.delay_kmax + 2 <= kThrSmem;
-  if (thr_fits)
-    for (uint32_t i = threadIdx.x; i < P.delay_kmax + 2; i += blockDim.x) s_thr[i] = P.delay_thr[i];
-  __syncthreads();
-  const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
-  if (inst >= P.num_instances) return;
-  const uint32_t tile = inst >> 5, lane = inst & 31;
-  TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32, lane};
-  uint32_t* sk = nullptr;
-  uint16_t* sd = nullptr;
-  if (QMODE == 2) {
-    const uint32_t warp = threadIdx.x >> 5, qcap = P.L.queue_cap;
-    uint32_t* base = s_queue + (size_t)warp * (qcap * 32 + qcap * 16);  // keys (qcap*32 words) + payload (qcap*32 halves)
-    sk = base + lane;
-    sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
-  }
-  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
-  if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
-  else core.init(P.seeds[inst]);
-  core.run();
-  core.finalize(inst);
-  if (RES) core.save_regs();
-}
 
 // ---------------------------------------------------------------------------------------------
 // handle
@@ -457,18 +404,29 @@ int lbft_run_until(lbft_sim* s, int64_t stop_clock) {
 
 }  // extern "C"
 
-// Which instantiation enqueue_kernel launches for this handle, spelled like the symbol ncu / cuobjdump show.
-static std::string kernel_name(const lbft_sim* s) {
+// Which instantiation this handle launches (host_setup.hpp decided wide vs thread-per-instance and the queue mode).
+static KernelSel select_kernel(const lbft_sim* s) {
+  KernelSel k{};
+  k.wide = s->hs.use_wide;
+  k.qmode = (int)s->P.L.queue_scan;
+  k.nmax = (k.qmode == 1 || k.qmode == 2) ? 16 : (s->N <= 16 ? 16 : (s->N <= 32 ? 32 : 64));
+  k.rec = s->P.record_rs != 0;
+  k.res = s->P.resumable != 0;
+  // the default four-author layout has a kernel instantiation with compile-time field offsets
   constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
   const bool plain_model = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0 &&
                            s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
-  const uint32_t q = s->P.L.queue_scan;
-  if (q == 2 && plain_model && !s->P.record_rs && !s->P.resumable && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0)
-    return "lbft_event_loop_kernel<16,2,true,false,false>";
-  const int nmax = (q == 1 || q == 2) ? 16 : (s->N <= 16 ? 16 : (s->N <= 32 ? 32 : 64));
+  k.fixed = !k.wide && k.qmode == 2 && plain_model && !k.rec && !k.res && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0;
+  return k;
+}
+// ... spelled like the symbol ncu / cuobjdump show.
+static std::string kernel_name(const lbft_sim* s) {
+  const KernelSel k = select_kernel(s);
   char buf[96];
-  snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%u,false,%s,%s>", nmax, q, s->P.record_rs ? "true" : "false",
-           s->P.resumable ? "true" : "false");
+  if (k.wide) snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d>", k.nmax, k.qmode);
+  else
+    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
+             k.res ? "true" : "false");
   return buf;
 }
 
@@ -477,34 +435,13 @@ static int enqueue_kernel(lbft_sim* s) {
   s->P.run_flags = (s->P.resumable && s->started) ? 1u : 0u;
   CUDA_TRY(cudaMemsetAsync(s->d_error, 0, sizeof(uint32_t), s->stream));
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
-#define LBFT_LAUNCH(NMAX, QM)                                                                                      \
-  do {                                                                                                             \
-    constexpr int T = LaunchShape<QM>::kThreads;                                                                   \
-    const uint32_t blocks = (s->I + T - 1) / T;                                                                    \
-    const size_t dyn = QM == 2 ? (size_t)(T / 32) * s->P.L.queue_cap * (32 * 4 + 32 * 2) : 0;                      \
-    if (s->P.record_rs && s->P.resumable) lbft_event_loop_kernel<NMAX, QM, false, true, true><<<blocks, T, dyn, s->stream>>>(s->P); \
-    else if (s->P.resumable) lbft_event_loop_kernel<NMAX, QM, false, false, true><<<blocks, T, dyn, s->stream>>>(s->P);          \
-    else if (s->P.record_rs) lbft_event_loop_kernel<NMAX, QM, false, true><<<blocks, T, dyn, s->stream>>>(s->P);                 \
-    else lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, s->stream>>>(s->P);                                                   \
-  } while (0)
-  // the default four-author layout has a kernel instantiation with compile-time field offsets
-  constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
-  const bool plain_model = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0 &&
-                           s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
-  if (s->P.L.queue_scan == 2 && plain_model && !s->P.record_rs && !s->P.resumable && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0) {
-    constexpr int T = LaunchShape<2>::kThreads;
-    lbft_event_loop_kernel<16, 2, true><<<(s->I + T - 1) / T, T, (size_t)(T / 32) * 64 * (32 * 4 + 32 * 2), s->stream>>>(s->P);
-  } else if (s->P.L.queue_scan == 2) LBFT_LAUNCH(16, 2);
-  else if (s->P.L.queue_scan == 1) LBFT_LAUNCH(16, 1);
-  else if (s->P.L.queue_scan == 3) {
-    if (s->N <= 16) LBFT_LAUNCH(16, 3);
-    else if (s->N <= 32) LBFT_LAUNCH(32, 3);
-    else LBFT_LAUNCH(64, 3);
-  } else if (s->N <= 16) LBFT_LAUNCH(16, 0);
-  else if (s->N <= 32) LBFT_LAUNCH(32, 0);
-  else LBFT_LAUNCH(64, 0);
-#undef LBFT_LAUNCH
-  CUDA_TRY(cudaGetLastError());
+  const KernelSel k = select_kernel(s);
+  cudaError_t e = k.wide ? launch_wide(k, s->P, s->stream)
+                  : k.fixed ? launch_fixed(k, s->P, s->stream)
+                  : (k.qmode == 1 || k.qmode == 2) ? launch_scan(k, s->P, s->stream)
+                  : k.qmode == 3 ? launch_calendar(k, s->P, s->stream)
+                                 : launch_heap(k, s->P, s->stream);
+  if (e != cudaSuccess) return set_error(LBFT_ERR_CUDA, std::string("kernel launch (") + kernel_name(s) + "): " + cudaGetErrorString(e));
   CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
   return LBFT_OK;
 }

@@ -37,10 +37,10 @@
 
 #if defined(__CUDACC__)
 #define LBFT_HD __host__ __device__ __forceinline__
-#define LBFT_COLD __host__ __device__ __noinline__
+#define LBFT_COLD inline __host__ __device__ __noinline__
 #else
 #define LBFT_HD inline
-#define LBFT_COLD __attribute__((noinline))
+#define LBFT_COLD inline __attribute__((noinline))
 #include <cmath>
 #endif
 
@@ -198,6 +198,29 @@ struct AuthorList<64> {
   }
 };
 
+// Per-warp shared-memory scratch of the warp-per-instance ("wide") kernel: the shuffled receiver list and the staged
+// normal deviates / delays of one fan-out.
+struct WideScratch {
+  double z[64];
+  uint16_t dly[64];
+  uint8_t list[64];
+};
+// AuthorList with its bytes in the warp's scratch (every lane performs the same writes).
+struct AuthorListShared {
+  uint8_t* a;
+  uint32_t len = 0;
+  LBFT_HD explicit AuthorListShared(uint8_t* p) : a(p) {}
+  LBFT_HD void clear() { len = 0; }
+  LBFT_HD void push(uint32_t x) { a[len++] = (uint8_t)x; }
+  LBFT_HD uint32_t get(uint32_t i) const { return a[i]; }
+  LBFT_HD void swap(uint32_t i, uint32_t j) { uint8_t t = a[i]; a[i] = a[j]; a[j] = t; }
+  LBFT_HD void fill_others(uint32_t n_nodes, uint32_t self) {
+    len = 0;
+    for (uint32_t i = 0; i < n_nodes; i++)
+      if (i != self) a[len++] = (uint8_t)i;
+  }
+};
+
 struct Actions {  // NodeUpdateActions, interfaces.rs:12-21 (should_send holds at most one author)
   int32_t next;
   int32_t send_to;
@@ -267,9 +290,25 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // RES: resumable run (LBFT_FLAG_RESUMABLE): the loop stops at P.stop_clock the way loop_until(max_clock) does
 // (simulator.rs:383-391: the first event beyond it is popped and dropped), the instance registers are saved to /
 // restored from the save area, and finalize() leaves the queue alone.
-template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false>
+// G: lanes that simulate ONE instance together.  G = 1: one thread per instance, 32 instances per warp (large batches).
+// G = 32 ("wide"): one warp per instance — every lane runs the same scalar state machine on the same values (all
+// branches are warp-uniform, so nothing ever diverges), and the data-parallel pieces (queue scan, per-receiver delay
+// lookup of a fan-out, per-author vectors, table clears) are split over the lanes.  For small batches and large
+// committees, where one thread per instance leaves the machine empty.
+template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, int G = 1>
 struct Core {
   static_assert(!(FIXED && (REC || RES)), "the compile-time layout has neither a round-switch table nor a save area");
+  static_assert(G == 1 || G == 32, "one thread or one warp per instance");
+  static_assert(G == 1 || !(FIXED || REC || RES), "the wide kernel has no fixed-layout / recording / resumable variants");
+  static constexpr bool WIDE = G > 1;
+  static constexpr int QS = WIDE ? 1 : 32;  // QMODE 2: stride between queue entries in shared memory (a column per lane / contiguous)
+  uint32_t wl = 0;            // this thread's lane inside the group (0 when G == 1)
+  WideScratch* ws = nullptr;  // wide kernel: the warp's scratch
+  LBFT_HD static void grp_sync() {
+#if defined(__CUDA_ARCH__)
+    if (WIDE) __syncwarp();
+#endif
+  }
   // Duplicate timers are accounted at push time instead of being queued (push_timer) only when every pop does not
   // matter individually: not while recording (each pop is a sampling point) and not in resumable runs (the event
   // dropped at a stop must be the one the reference drops).
@@ -350,21 +389,22 @@ struct Core {
       if (o.accepted) return o.x;
     }
   }
+  // (exp(mu + sigma*z) as i64) == number of thresholds <= z; the thresholds were bisected on the host
+  // with the host libm, so this is exact.  Any starting guess works; the walk fixes it up.
+  LBFT_HD int32_t delay_from_z(double z) const {
+    float g = expf((float)P.mu + (float)P.sigma * (float)z);
+    int32_t k = g < (float)P.delay_kmax ? (int32_t)g : (int32_t)P.delay_kmax;
+    if (k < 0) k = 0;
+    while (z >= thr[k + 1]) k++;
+    while (z < thr[k]) k--;
+    return k;
+  }
   // GlobalTime::add_delay (simulator.rs:110-118): returns the delay in ms.
   LBFT_HD int32_t sample_delay() {
     if (!FIXED && P.delay_kind == 1u) return (int32_t)(P.uni_lo + gen_range_u64(P.uni_span));
     double z = standard_normal();
     if (!FIXED && P.delay_const) return (int32_t)P.delay_const_value;  // sigma == 0: exp(mu) evaluated by the host libm
-    if (FIXED || P.delay_kmax) {
-      // (exp(mu + sigma*z) as i64) == number of thresholds <= z; the thresholds were bisected on the host
-      // with the host libm, so this is exact.  Any starting guess works; the walk fixes it up.
-      float g = expf((float)P.mu + (float)P.sigma * (float)z);
-      int32_t k = g < (float)P.delay_kmax ? (int32_t)g : (int32_t)P.delay_kmax;
-      if (k < 0) k = 0;
-      while (z >= thr[k + 1]) k++;
-      while (z < thr[k]) k--;
-      return k;
-    }
+    if (FIXED || P.delay_kmax) return delay_from_z(z);
     int64_t r = delay_via_exp(P.mu, P.sigma, z);
     if (r & (1LL << 62)) status |= ST_DELAY_NEAR_INT;
     if (r & (1LL << 61)) status |= ST_TIME_OVERFLOW;
@@ -517,8 +557,8 @@ struct Core {
     }
     if (QMODE == 2) {
       // stamps are unique, so a 32-bit key decides every comparison; the payload word is not compared
-      sk[qsize * 32] = ((uint32_t)time << 18) | ((3u - kind) << 16) | (st & 0xffffu);
-      sd[qsize * 32] = (uint16_t)((((data >> 16) & 0xffu) << 8) | (((data >> 8) & 0xfu) << 4) | (data & 0xfu));
+      sk[qsize * QS] = ((uint32_t)time << 18) | ((3u - kind) << 16) | (st & 0xffffu);
+      sd[qsize * QS] = (uint16_t)((((data >> 16) & 0xffu) << 8) | (((data >> 8) & 0xfu) << 4) | (data & 0xfu));
       qsize++;
       if (qsize > max_queue) max_queue = qsize;
       return true;
@@ -572,6 +612,33 @@ struct Core {
       qsize--;
       return;
     }
+    if (QMODE == 2 && WIDE) {
+#if defined(__CUDA_ARCH__)
+      // the warp scans its one queue together: lane l looks at entries l, l + 32, ...; keys are unique (creation stamps)
+      __syncwarp();  // entries pushed by this iteration's sends
+      const uint32_t n = qsize;
+      uint32_t best = 0xffffffffu, bi = 0;
+      for (uint32_t j = wl; j < n; j += 32) {
+        const uint32_t k0 = sk[j];
+        if (k0 < best) { best = k0; bi = j; }
+      }
+      const uint32_t mn = __reduce_min_sync(0xffffffffu, best);
+      const uint32_t src = (uint32_t)__ffs((int)__ballot_sync(0xffffffffu, best == mn)) - 1u;
+      bi = __shfl_sync(0xffffffffu, bi, (int)src);
+      const uint32_t lo = sd[bi];
+      qsize = n - 1;
+      __syncwarp();  // everyone has read sd[bi] / its share of the keys
+      if (bi != n - 1) {
+        sk[bi] = sk[n - 1];
+        sd[bi] = sd[n - 1];
+      }
+      time = (int32_t)(mn >> 18);
+      kind = 3u - ((mn >> 16) & 3u);
+      const uint32_t slot = lo >> 8;
+      data = (lo & 0xfu) | (((lo >> 4) & 0xfu) << 8) | ((slot == 0xffu ? PAY_NONE : slot) << 16);
+#endif
+      return;
+    }
     if (QMODE == 2) {
       uint32_t best = sk[0], bi = 0;
       const uint32_t n = qsize;
@@ -599,6 +666,35 @@ struct Core {
       kind = 3u - ((best >> 16) & 3u);
       uint32_t slot = lo >> 8;
       data = (lo & 0xfu) | (((lo >> 4) & 0xfu) << 8) | ((slot == 0xffu ? PAY_NONE : slot) << 16);
+      return;
+    }
+    if (QMODE == 1 && WIDE) {
+#if defined(__CUDA_ARCH__)
+      __syncwarp();
+      const uint64_t* q = m.at64(L.heap_time);
+      const uint32_t n = qsize;
+      uint64_t best = ~0ULL;
+      uint32_t bi = 0;
+      for (uint32_t j = wl; j < n; j += 32) {
+        const uint64_t k0 = q[(size_t)j * S];
+        if (k0 < best) { best = k0; bi = j; }
+      }
+      // 64-bit minimum over the warp: high words first, then low words among the lanes that hold the minimal high word
+      const uint32_t hi = __reduce_min_sync(0xffffffffu, (uint32_t)(best >> 32));
+      const uint32_t lo32 = __reduce_min_sync(0xffffffffu, (uint32_t)(best >> 32) == hi ? (uint32_t)best : 0xffffffffu);
+      const uint64_t mn = ((uint64_t)hi << 32) | lo32;
+      const uint32_t src = (uint32_t)__ffs((int)__ballot_sync(0xffffffffu, best == mn)) - 1u;
+      bi = __shfl_sync(0xffffffffu, bi, (int)src);
+      qsize = n - 1;
+      uint64_t* qw = m.at64(L.heap_time);
+      const uint64_t last = qw[(size_t)(n - 1) * S];
+      __syncwarp();
+      if (bi != n - 1) qw[(size_t)bi * S] = last;
+      time = (int32_t)(mn >> 40);
+      kind = 3u - ((uint32_t)(mn >> 38) & 3u);
+      const uint32_t lo = (uint32_t)mn & 0xffffu, slot = lo >> 8;
+      data = (lo & 0xfu) | (((lo >> 4) & 0xfu) << 8) | ((slot == 0xffu ? PAY_NONE : slot) << 16);
+#endif
       return;
     }
     if (QMODE == 1) {
@@ -761,7 +857,9 @@ struct Core {
     d.f[F_TOW] += P.c_weights[author];
     if (d.f[F_TOW] >= P.quorum) {
       d.tcmask = d.tmask;
-      for (uint32_t i = 0; i < L.hcbr_words; i++) d.nb[(L.n_tchcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
+      grp_sync();  // the st_u16 above is read by another lane below
+      for (uint32_t i = wl; i < L.hcbr_words; i += G) d.nb[(L.n_tchcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
+      grp_sync();
       d.f[F_TC_ROUND] = d.f[F_CUR];
       d.f[F_FLAGS] |= FL_HAS_TC;
       d.f[F_HTC] = d.f[F_CUR];
@@ -949,9 +1047,10 @@ struct Core {
       }
     } else {
       if (has_tc)
-        for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_tchcbr + i) * S] = d.nb[(L.n_tchcbr + i) * S];
+        for (uint32_t i = wl; i < L.hcbr_words; i += G) pb[(L.p_tchcbr + i) * S] = d.nb[(L.n_tchcbr + i) * S];
       if (d.tmask)
-        for (uint32_t i = 0; i < L.hcbr_words; i++) pb[(L.p_curhcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
+        for (uint32_t i = wl; i < L.hcbr_words; i += G) pb[(L.p_curhcbr + i) * S] = d.nb[(L.n_thcbr + i) * S];
+      grp_sync();
     }
   }
   // DataSyncNode::handle_notification (data_sync.rs:113-177).  Returns should_sync.
@@ -981,6 +1080,9 @@ struct Core {
       mask_t mask = which ? curm : tcm;
       if (round != 0 && round == d.f[F_CUR]) {
         const uint32_t* hp = pb + (which ? L.p_curhcbr : L.p_tchcbr) * S;
+        // an author already in current_timeouts is rejected by insert_timeout whatever else holds ("already have it",
+        // record_store.rs:407-411), and the set only grows while the round stands: skip them without the call
+        mask &= ~d.tmask;
         while (mask) {
           uint32_t a = NMAX > 32 ? ctz64((uint64_t)mask) : ctz32((uint32_t)mask);
           mask &= mask - 1;
@@ -1005,13 +1107,20 @@ struct Core {
     return false;
   }
   LBFT_HD bool schedule_network_event(uint32_t kind, uint32_t receiver, uint32_t sender, uint32_t slot) {
-    int32_t t = clock + sample_delay();
+    return enqueue_network_event(kind, receiver, sender, slot, sample_delay());
+  }
+  LBFT_HD bool enqueue_network_event(uint32_t kind, uint32_t receiver, uint32_t sender, uint32_t slot, int32_t delay) {
+    int32_t t = clock + delay;
     if (L.part_windows && partitioned(receiver, sender)) {
       stamp++;
       return false;
     }
     return push_event(t, kind, receiver | (sender << 8) | (slot << 16));
   }
+  template <bool W = WIDE>
+  LBFT_HD typename std::enable_if<W, AuthorListShared>::type make_list() const { return AuthorListShared(ws->list); }
+  template <bool W = WIDE>
+  LBFT_HD typename std::enable_if<!W, AuthorList<(NMAX <= 16 ? 16 : 64)>>::type make_list() const { return AuthorList<(NMAX <= 16 ? 16 : 64)>(); }
   LBFT_HD void push_timer(uint32_t n, NodeRegs& d, int32_t t) {
     // (not while recording round switches: every pop is a DataWriter sampling point, data_writer.rs:34-50, so the
     // duplicate has to be popped where the reference pops it)
@@ -1045,10 +1154,12 @@ struct Core {
       rs_pend = 0;
       for (uint32_t w = 0; w < N * (L.round_cap + 1); w++) m.st(rs_table_base(L) + w, 0);
     }
+    // (table clears are split over the lanes of the group; G == 1: wl == 0, the plain loops)
     if (QMODE == 3)
-      for (uint32_t w = 0; w < (L.cal_times + 7) / 8; w++) m.st(L.cal_kmask + w, 0);
-    for (uint32_t w = 0; w < N * L.node_words; w++) m.st(L.node_base + w, 0);
-    for (uint32_t w = 0; w < 2 * L.rset_words; w++) m.st(L.created_base + w, 0);
+      for (uint32_t w = wl; w < (L.cal_times + 7) / 8; w += G) m.st(L.cal_kmask + w, 0);
+    for (uint32_t w = wl; w < N * L.node_words; w += G) m.st(L.node_base + w, 0);
+    for (uint32_t w = wl; w < 2 * L.rset_words; w += G) m.st(L.created_base + w, 0);
+    grp_sync();
     // EXTENSION D.3: partition plan from a separate stream; must match oracle_capi.cpp make_partition_plan
     if (L.part_windows) {
       uint64_t k0 = s0, k1 = s1, k2 = s2, k3 = s3;
@@ -1152,7 +1263,7 @@ struct Core {
       // cost of an iteration is the number of passes x the longest list in each.  Two exact foldings keep that
       // small: a Request event's single Response send, and a query-all fan-out whose notification list is empty,
       // run inside the notification pass (nothing of the same instance lies between them in the RNG stream).
-      AuthorList<(NMAX <= 16 ? 16 : 64)> list;
+      typename std::conditional<WIDE, AuthorListShared, AuthorList<(NMAX <= 16 ? 16 : 64)>>::type list = make_list();
       bool query_pending = a.query_all;
       // (a lane only enters the passes it has something to do in: pass 0 when it owes a sync request, pass 2 when a
       // query-all is still pending after pass 1)
@@ -1191,11 +1302,22 @@ struct Core {
           prefetch_hcbr(d, hc);
         }
         uint32_t queued = 0;
+        // Wide kernel, table-served LogNormal delay: the normal deviates of the fan-out are drawn first (the RNG stream is
+        // sequential), then each lane turns its share of them into delays, then the events are queued in list order.
+        // Nothing else draws from the stream or takes a creation stamp in between, so the order of both is unchanged.
+        const bool staged = WIDE && list.len > 1 && P.delay_kind == 0u && !P.delay_const && P.delay_kmax != 0;
+        if (staged) {
+          for (uint32_t i = 0; i < list.len; i++) ws->z[i] = standard_normal();
+          grp_sync();
+          for (uint32_t i = wl; i < list.len; i += G) ws->dly[i] = (uint16_t)delay_from_z(ws->z[i]);
+          grp_sync();
+        }
 #pragma unroll 1
         for (uint32_t i = 0; i < list.len; i++) {
           uint32_t other = list.get(i);
           uint32_t ev_recv = to_other ? other : receiver, ev_send = to_other ? receiver : other;
-          if (schedule_network_event(ev_kind, ev_recv, ev_send, pslot)) queued++;
+          if (staged ? enqueue_network_event(ev_kind, ev_recv, ev_send, pslot, (int32_t)ws->dly[i])
+                     : schedule_network_event(ev_kind, ev_recv, ev_send, pslot)) queued++;
         }
         if (to_other && pslot != PAY_NONE) {
           if (queued) write_notification(receiver, d, pslot, queued, hc);

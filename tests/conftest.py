@@ -22,3 +22,11 @@ def oracle():
 def hostcore():
     from tests import support
     return support.HostCore()
+
+
+@pytest.fixture(params=["thread", "wide"])
+def kernel_choice(request, monkeypatch):
+    """Run a GPU test once per kernel family: LBFT_FORCE_KERNEL (read by lbft_create) overrides the host's automatic choice
+    between the thread-per-instance and the warp-per-instance kernel."""
+    monkeypatch.setenv("LBFT_FORCE_KERNEL", request.param)
+    return request.param

@@ -14,7 +14,7 @@ def gpu_runner(seeds, n, max_clock, **kw):
     return res
 
 
-def test_fuzz_gpu_vs_oracle(oracle):
+def test_fuzz_gpu_vs_oracle(oracle, kernel_choice):
     rng = np.random.default_rng(20260922)
     reran = 0
     for _ in range(120):

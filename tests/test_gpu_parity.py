@@ -80,10 +80,11 @@ CASES = [
 
 
 @pytest.mark.parametrize("seed0,count,nodes,max_clock,extra", CASES)
-def test_gpu_matches_oracle(oracle, seed0, count, nodes, max_clock, extra):
+def test_gpu_matches_oracle(oracle, kernel_choice, seed0, count, nodes, max_clock, extra):
     seeds = np.arange(seed0, seed0 + count, dtype=np.uint64)
     o = oracle.run(seeds, nodes, max_clock, **extra)
     sim, g = gpu_run(seeds, nodes, max_clock, **dict(extra))
+    assert sim.kernel_info().startswith("lbft_wide_kernel" if kernel_choice == "wide" else "lbft_event_loop_kernel")
     assert ((g.status & ~np.uint32(64)) == 1).all(), np.unique(g.status)
     assert_same(o, g, "N=%d" % nodes)
     # the commit logs themselves, for a few (instance, node) pairs
@@ -190,7 +191,7 @@ EXT_CASES = [
 
 
 @pytest.mark.parametrize("name,seed0,count,nodes,max_clock,extra", EXT_CASES)
-def test_gpu_extensions_match_oracle(oracle, name, seed0, count, nodes, max_clock, extra):
+def test_gpu_extensions_match_oracle(oracle, kernel_choice, name, seed0, count, nodes, max_clock, extra):
     seeds = np.arange(seed0, seed0 + count, dtype=np.uint64)
     o = oracle.run(seeds, nodes, max_clock, **extra)
     sim, g = gpu_run(seeds, nodes, max_clock, **dict(extra))
@@ -202,7 +203,7 @@ def test_gpu_extensions_match_oracle(oracle, name, seed0, count, nodes, max_cloc
 
 
 @pytest.mark.parametrize("nodes,count,seed0", [(3, 4096, 10_000), (4, 8192, 20_000), (5, 2048, 30_000), (7, 1024, 40_000)])
-def test_wide_seed_sweep_matches_oracle(oracle, nodes, count, seed0):
+def test_wide_seed_sweep_matches_oracle(oracle, kernel_choice, nodes, count, seed0):
     # every instance of a few thousand seeds, compared in full (the oracle needs ~1 ms per instance and core)
     seeds = np.arange(seed0, seed0 + count, dtype=np.uint64)
     o = oracle.run(seeds, nodes, 1000)
