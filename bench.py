@@ -322,7 +322,7 @@ def measure_side_config(cfg_id, device, steps=2, warmup=1):
            "e2e": e2e_rounds / e2e_s, "steps": steps, "warmup": warmup,
            "events_per_s": float(res.counters[:, 0:4].sum()) / (k_ms * 1e-3),
            "roofline": roofline_block(cfg_id, cfg, I, res.counters, k_ms, kernel),
-           "flagged_instances": int(((res.status & 0xBE) != 0).sum()),
+           "flagged_instances": int(((res.status & 0x9E) != 0).sum()),
            "parity": parity, "cpu_baseline": base, "e2e_over_cpu": (e2e_rounds / e2e_s) / base["value"]}
     sim.close()
     return out
@@ -443,7 +443,7 @@ def main():
         last = sim.download(strict=False)
         sharded.gather(last)
         rounds_dev += float(last.active_rounds.sum())
-        flagged += int(((last.status & 0xBE) != 0).sum())  # any LBFT_ST_ERROR_MASK bit (capacity / invariant / epoch)
+        flagged += int(((last.status & 0x9E) != 0).sum())  # any LBFT_ST_ERROR_MASK bit (capacity / invariant / epoch)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 

@@ -47,14 +47,15 @@ enum {
   LBFT_ST_QUEUE_OVERFLOW = 1u << 2,   /* pending-event queue reached queue_cap                    */
   LBFT_ST_PAYLOAD_OVERFLOW = 1u << 3, /* in-flight notification pool reached payload_cap          */
   LBFT_ST_INVARIANT = 1u << 4,        /* a layout invariant was violated          */
-  LBFT_ST_EPOCH_CHANGE = 1u << 5,     /* commit count reached commands_per_epoch (unsupported)    */
+  LBFT_ST_EPOCH_CHANGE = 1u << 5,     /* advisory: the instance went through an epoch change      */
+                                      /* (commands_per_epoch reached, node.rs:329-348)            */
   LBFT_ST_DELAY_NEAR_INT = 1u << 6,   /* a LogNormal sample landed within 1e-9 of an integer: the */
                                       /* truncation may depend on the libm's last ulp (advisory)  */
   LBFT_ST_TIME_OVERFLOW = 1u << 7     /* a time left the 31-bit range of the device encoding      */
 };
 #define LBFT_ST_ERROR_MASK                                                                       \
   (LBFT_ST_ROUND_OVERFLOW | LBFT_ST_QUEUE_OVERFLOW | LBFT_ST_PAYLOAD_OVERFLOW | LBFT_ST_INVARIANT | \
-   LBFT_ST_EPOCH_CHANGE | LBFT_ST_TIME_OVERFLOW)
+   LBFT_ST_TIME_OVERFLOW)
 
 /* One row of SimulatedContext::committed_history(): (Command{proposer,index}, NodeTime)
  * (simulated_context.rs:31-35, 98-100). */

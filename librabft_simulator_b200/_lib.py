@@ -46,7 +46,7 @@ LBFT_OK = 0
 LBFT_ERR_CAPACITY = -4
 ST_DONE, ST_ROUND_OVERFLOW, ST_QUEUE_OVERFLOW, ST_PAYLOAD_OVERFLOW = 1, 2, 4, 8
 ST_INVARIANT, ST_EPOCH_CHANGE, ST_DELAY_NEAR_INT, ST_TIME_OVERFLOW = 16, 32, 64, 128
-ST_ERROR_MASK = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST_INVARIANT | ST_EPOCH_CHANGE | ST_TIME_OVERFLOW
+ST_ERROR_MASK = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST_INVARIANT | ST_TIME_OVERFLOW
 
 EXPORTS = [
     "lbft_create", "lbft_run", "lbft_run_async", "lbft_wait", "lbft_commit_logs", "lbft_upload", "lbft_run_device", "lbft_download", "lbft_commit_counts",

@@ -166,7 +166,19 @@ struct HostSetup {
     p.resumable = (c.flags & LBFT_FLAG_RESUMABLE) ? 1u : 0u;
     p.stop_clock = p.max_clock;
     p.run_flags = 0;
-    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0);
+    // Epochs (node.rs:329-348): a node commits at most one command per round, so commands_per_epoch >= round_cap can never
+    // be reached and the layout stays single-epoch (every BASELINE configuration).  Otherwise the per-round tables get
+    // `epochs` spans of round_cap rounds each (global round id = epoch * rspan + round).
+    uint32_t epochs = 1;
+    if (c.commands_per_epoch < rcap) {
+      epochs = (uint32_t)(rcap / c.commands_per_epoch) + 2;
+      if (epochs > MAX_EPOCHS) epochs = MAX_EPOCHS;
+      while (epochs > 2 && (uint64_t)epochs * rcap > 32768) epochs--;
+      if (qcap < (epochs * rcap + 1) / 2 && qscan) qcap = (epochs * rcap + 1) / 2;  // read-out scratch (see above)
+      if (qcap < epochs * rcap && !qscan) qcap = pow2_ceil(epochs * rcap);
+      if (qscan == 2 && qcap > 64) qscan = 1;
+    }
+    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0, epochs);
     // One thread per instance needs tens of thousands of instances to fill a B200 (65 536 x 4 authors is exactly one wave of
     // warps) and serialises the 32 instances of a warp through every fan-out; one WARP per instance (lbft_wide_kernel) has
     // no cross-instance divergence and splits fan-outs, queue scans and per-author vectors over its lanes.  Measured

@@ -27,6 +27,7 @@ static_assert(LBFT_SAME(ST_DONE, LBFT_ST_DONE) && LBFT_SAME(ST_ROUND_OVERFLOW, L
                   LBFT_SAME(ST_DELAY_NEAR_INT, LBFT_ST_DELAY_NEAR_INT) && LBFT_SAME(ST_TIME_OVERFLOW, LBFT_ST_TIME_OVERFLOW),
               "status bits out of sync with include/lbft.h");
 static_assert(sizeof(lbft_instance_counters) == 12 * sizeof(uint32_t), "counter layout");
+static_assert(LBFT_SAME(ST_ERROR_BITS, LBFT_ST_ERROR_MASK), "error mask out of sync with include/lbft.h");
 
 // ---------------------------------------------------------------------------------------------
 // handle
@@ -246,9 +247,9 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
   CREATE_TRY(dev_alloc(s, &s->d_seeds, I));
   CREATE_TRY(dev_alloc(s, &s->d_zx, 257));
   CREATE_TRY(dev_alloc(s, &s->d_zf, 257));
-  CREATE_TRY(dev_alloc(s, &s->d_leader, L.round_cap + 1));
-  CREATE_TRY(dev_alloc(s, &s->d_duration, L.round_cap + 1));
-  CREATE_TRY(dev_alloc(s, &s->d_period, L.round_cap + 1));
+  CREATE_TRY(dev_alloc(s, &s->d_leader, s->hs.leader.size()));
+  CREATE_TRY(dev_alloc(s, &s->d_duration, s->hs.duration.size()));
+  CREATE_TRY(dev_alloc(s, &s->d_period, s->hs.period.size()));
   CREATE_TRY(dev_alloc(s, &s->d_weights, N));
   if (!s->hs.delay_thr.empty()) CREATE_TRY(dev_alloc(s, &s->d_delay_thr, s->hs.delay_thr.size()));
   CREATE_TRY(dev_alloc(s, &s->d_state, tiles * L.total_words * s->stride));
@@ -274,9 +275,9 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
   // launch-invariant tables
   CREATE_TRY(cudaMemcpy(s->d_zx, s->hs.zig_x.data(), 257 * sizeof(double), cudaMemcpyHostToDevice));
   CREATE_TRY(cudaMemcpy(s->d_zf, s->hs.zig_f.data(), 257 * sizeof(double), cudaMemcpyHostToDevice));
-  CREATE_TRY(cudaMemcpy(s->d_leader, s->hs.leader.data(), L.round_cap + 1, cudaMemcpyHostToDevice));
-  CREATE_TRY(cudaMemcpy(s->d_duration, s->hs.duration.data(), (L.round_cap + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CREATE_TRY(cudaMemcpy(s->d_period, s->hs.period.data(), (L.round_cap + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_leader, s->hs.leader.data(), s->hs.leader.size(), cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_duration, s->hs.duration.data(), s->hs.duration.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CREATE_TRY(cudaMemcpy(s->d_period, s->hs.period.data(), s->hs.period.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   CREATE_TRY(cudaMemcpy(s->d_weights, s->hs.weights.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
   if (s->d_delay_thr)
     CREATE_TRY(cudaMemcpy(s->d_delay_thr, s->hs.delay_thr.data(), s->hs.delay_thr.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -584,14 +585,21 @@ int lbft_commit_log(lbft_sim* s, uint32_t instance, uint32_t node, lbft_commit* 
   CUDA_TRY(cudaMemcpy2D(chain.data(), sizeof(uint32_t), src, S * sizeof(uint32_t), sizeof(uint32_t), chain.size(), cudaMemcpyDeviceToHost));
   uint32_t lc = s->res[s->done].lc_round[(size_t)instance * s->N + node];
   uint32_t count = s->res[s->done].commit_counts[(size_t)instance * s->N + node];
+  // epochs > 1: the parent of an epoch's first block is the block whose state is the epoch's initial state
+  std::vector<uint32_t> einit(L.epochs, 0);
+  if (L.epochs > 1)
+    CUDA_TRY(cudaMemcpy2D(einit.data(), sizeof(uint32_t), s->d_state + ((size_t)tile * L.total_words + L.einit_base) * S + lane,
+                          S * sizeof(uint32_t), sizeof(uint32_t), L.epochs, cudaMemcpyDeviceToHost));
   std::vector<lbft_commit> log(count);
   uint32_t i = count;
-  for (uint32_t r = lc; r != 0 && i > 0; r = chain[2 * r] & 0xffffu) {
+  for (uint32_t r = lc; r != 0 && i > 0;) {
     if (r >= L.round_cap) return set_error(LBFT_ERR_STATE, "corrupt chain table");
     --i;
-    log[i].proposer = s->hs.leader[r];
+    log[i].proposer = s->hs.leader[r % L.rspan];
     log[i].index = chain[2 * r] >> 16;
     log[i].time = (int64_t)(int32_t)chain[2 * r + 1];
+    const uint32_t p = chain[2 * r] & 0xffffu, e = r / L.rspan;
+    r = p ? e * L.rspan + p : einit[e];
   }
   if (i != 0) return set_error(LBFT_ERR_STATE, "chain shorter than the commit count");
   *n = count;
@@ -630,12 +638,13 @@ __global__ void lbft_commit_logs_kernel(const __grid_constant__ Params P, uint32
     const uint32_t c0 = tb[(size_t)(L.chain_base + 2 * r) * stride];
     if (k < cap) {
       lbft_commit e;
-      e.proposer = P.leader[r];
+      e.proposer = P.leader[r % L.rspan];
       e.index = c0 >> 16;
       e.time = (int64_t)(int32_t)tb[(size_t)(L.chain_base + 2 * r + 1) * stride];
       row[k] = e;
     }
-    r = c0 & 0xffffu;
+    const uint32_t p = c0 & 0xffffu, ep = r / L.rspan;
+    r = p ? ep * L.rspan + p : (L.epochs > 1 ? tb[(size_t)(L.einit_base + ep) * stride] : 0u);
   }
   uint32_t empty = 0;
   for (uint32_t n = 0; n < N; n++) empty += cc[n] == 0 ? (lc[n] == 0 ? 1u : 0x10000u) : 0u;
@@ -691,7 +700,7 @@ int lbft_round_switches(lbft_sim* s, uint32_t instance, lbft_round_switch* out, 
   CUDA_TRY(cudaMemcpy2D(table.data(), sizeof(uint32_t), src, S * sizeof(uint32_t), sizeof(uint32_t), table.size(), cudaMemcpyDeviceToHost));
   size_t k = 0;
   for (uint32_t node = 0; node < s->N; node++)
-    for (uint32_t r = 0; r < row; r++) {
+    for (uint32_t r = 1; r < row; r++) {  // slot 0 is the per-node maximum, not a switch
       const uint32_t w = table[(size_t)node * row + r];
       if (!w) continue;
       if (k < cap) out[k] = lbft_round_switch{node, r, (int64_t)(w - 1u)};

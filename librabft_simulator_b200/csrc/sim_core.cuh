@@ -57,7 +57,7 @@ enum : uint32_t {
   ST_DELAY_NEAR_INT = 1u << 6,
   ST_TIME_OVERFLOW = 1u << 7,
   ST_FATAL = ST_ROUND_OVERFLOW | ST_QUEUE_OVERFLOW | ST_PAYLOAD_OVERFLOW | ST_TIME_OVERFLOW,
-  ST_ERROR_BITS = ST_FATAL | ST_INVARIANT | ST_EPOCH_CHANGE  // == LBFT_ST_ERROR_MASK (static_asserted in lbft_api.cu)
+  ST_ERROR_BITS = ST_FATAL | ST_INVARIANT  // == LBFT_ST_ERROR_MASK (static_asserted in lbft_api.cu); ST_EPOCH_CHANGE is advisory
 };
 
 constexpr int32_t NODE_TIME_NEVER = 0x7fffffff;
@@ -435,10 +435,21 @@ struct Core {
   LBFT_HD void mbit_set(uint32_t w, uint32_t r) const { m.st(w + (r >> 5), m.ld(w + (r >> 5)) | (1u << (r & 31))); }
   // previous-QC round of block r.  The last few proposals of the instance are kept in a 4-entry direct-mapped
   // register cache (written through at propose time), which serves nearly every lookup without a dependent load.
-  LBFT_HD uint32_t chain_prev(uint32_t r) const {
-    uint32_t e = (r & 2) ? ((r & 1) ? cc3 : cc2) : ((r & 1) ? cc1 : cc0);
-    if ((e >> 16) == r) return e & 0xffffu;
-    return m.ld(L.chain_base + 2 * r) & 0xffffu;
+  // (g is a GLOBAL round id, epoch * rspan + round; the value returned is the previous QC's round inside the same epoch,
+  // 0 = the epoch's initial state)
+  LBFT_HD uint32_t chain_prev(uint32_t g) const {
+    uint32_t e = (g & 2) ? ((g & 1) ? cc3 : cc2) : ((g & 1) ? cc1 : cc0);
+    if ((e >> 16) == g) return e & 0xffffu;
+    return m.ld(L.chain_base + 2 * g) & 0xffffu;
+  }
+  // Epochs (node.rs:329-348): only configurations whose commands_per_epoch can be reached carry the machinery.
+  LBFT_HD bool multi() const { return !FIXED && L.epochs > 1; }
+  // GLOBAL id of the block whose state block g was executed on: its previous QC's block, or the epoch's initial state.
+  LBFT_HD uint32_t chain_parent(uint32_t g) const {
+    const uint32_t p = chain_prev(g);
+    if (!multi()) return p;
+    const uint32_t e = g / L.rspan;
+    return p ? e * L.rspan + p : m.ld(L.einit_base + e);
   }
   LBFT_HD void chain_cache_put(uint32_t r, uint32_t prev) {
     uint32_t e = (r << 16) | prev;
@@ -456,8 +467,10 @@ struct Core {
     uint32_t cw;                    // index of the cached bitset word
     uint32_t chb, chq, cpd;         // cached words: block known / QC known / state pending
     uint32_t dirty;                 // bit0 chb, bit1 chq, bit2 cpd modified
+    uint32_t gb;                    // epoch_id * rspan: global id of this node's round 0 (0 in single-epoch layouts)
     uint32_t* nb;                   // this node's block in the tile
   };
+  LBFT_HD static uint32_t epoch_of(const NodeRegs& d) { return (d.f[F_FLAGS] >> FL_EPOCH_SHIFT) & FL_EPOCH_BITS; }
   LBFT_HD void load_node(uint32_t n, NodeRegs& d) {
     uint32_t* nb = m.at(nbase(n));
     d.nb = nb;
@@ -470,7 +483,8 @@ struct Core {
     d.chb = nb[(L.n_hasblk + win) * S];
     d.chq = nb[(L.n_hasqc + win) * S];
     d.cpd = nb[(L.n_pend + win) * S];
-    uint32_t want = d.f[F_CUR] >> 5;
+    d.gb = multi() ? epoch_of(d) * L.rspan : 0u;
+    uint32_t want = (d.gb + d.f[F_CUR]) >> 5;
     if (want != win) {
       d.chb = nb[(L.n_hasblk + want) * S];
       d.chq = nb[(L.n_hasqc + want) * S];
@@ -494,9 +508,10 @@ struct Core {
   LBFT_HD uint32_t bword(const NodeRegs& d, uint32_t base, uint32_t cached, uint32_t r) const {
     return (r >> 5) == d.cw ? cached : d.nb[(base + (r >> 5)) * S];
   }
-  LBFT_HD bool has_blk(const NodeRegs& d, uint32_t r) const { return (bword(d, L.n_hasblk, d.chb, r) >> (r & 31)) & 1u; }
-  LBFT_HD bool has_qc(const NodeRegs& d, uint32_t r) const { return (bword(d, L.n_hasqc, d.chq, r) >> (r & 31)) & 1u; }
-  LBFT_HD bool is_pend(const NodeRegs& d, uint32_t r) const { return (bword(d, L.n_pend, d.cpd, r) >> (r & 31)) & 1u; }
+  // (r: a round of the node's CURRENT epoch; the bitsets are indexed by global id)
+  LBFT_HD bool has_blk(const NodeRegs& d, uint32_t r) const { r += d.gb; return (bword(d, L.n_hasblk, d.chb, r) >> (r & 31)) & 1u; }
+  LBFT_HD bool has_qc(const NodeRegs& d, uint32_t r) const { r += d.gb; return (bword(d, L.n_hasqc, d.chq, r) >> (r & 31)) & 1u; }
+  LBFT_HD bool is_pend(const NodeRegs& d, uint32_t r) const { r += d.gb; return (bword(d, L.n_pend, d.cpd, r) >> (r & 31)) & 1u; }
   LBFT_HD void bput(NodeRegs& d, uint32_t base, uint32_t& cached, uint32_t dirty_bit, uint32_t r, bool on) const {
     uint32_t bit = 1u << (r & 31);
     if ((r >> 5) == d.cw) {
@@ -507,9 +522,9 @@ struct Core {
       *p = on ? (*p | bit) : (*p & ~bit);
     }
   }
-  LBFT_HD void set_blk(NodeRegs& d, uint32_t r) const { bput(d, L.n_hasblk, d.chb, 1u, r, true); }
-  LBFT_HD void set_qc(NodeRegs& d, uint32_t r) const { bput(d, L.n_hasqc, d.chq, 2u, r, true); }
-  LBFT_HD void set_pend(NodeRegs& d, uint32_t r, bool on) const { bput(d, L.n_pend, d.cpd, 4u, r, on); }
+  LBFT_HD void set_blk(NodeRegs& d, uint32_t r) const { bput(d, L.n_hasblk, d.chb, 1u, d.gb + r, true); }
+  LBFT_HD void set_qc(NodeRegs& d, uint32_t r) const { bput(d, L.n_hasqc, d.chq, 2u, d.gb + r, true); }
+  LBFT_HD void set_pend(NodeRegs& d, uint32_t r, bool on) const { bput(d, L.n_pend, d.cpd, 4u, d.gb + r, on); }
 
   LBFT_HD static uint32_t election(const NodeRegs& d) { return (d.f[F_FLAGS] & FL_ELECTION_MASK) >> FL_ELECTION_SHIFT; }
   LBFT_HD static void set_election(NodeRegs& d, uint32_t e) { d.f[F_FLAGS] = (d.f[F_FLAGS] & ~FL_ELECTION_MASK) | (e << FL_ELECTION_SHIFT); }
@@ -793,7 +808,7 @@ struct Core {
   // update_current_round, record_store.rs:207-219
   LBFT_HD void update_current_round(NodeRegs& d, uint32_t round) {
     if (round <= d.f[F_CUR]) return;
-    if (round >= L.round_cap) { status |= ST_ROUND_OVERFLOW; return; }
+    if (round >= L.rspan) { status |= ST_ROUND_OVERFLOW; return; }
     d.f[F_CUR] = round;
     d.f[F_FLAGS] &= ~(FL_PROPOSED | FL_ELECTION_MASK);
     d.tmask = 0;
@@ -804,6 +819,12 @@ struct Core {
   // Is the execution state of the block certified by QC `prev` (0 = the epoch's initial state)
   // available to SimulatedContext::compute?  simulated_context.rs:102-108, 128-157
   LBFT_HD bool state_available(const NodeRegs& d, uint32_t prev) const {
+    if (multi()) {
+      // prev == 0: the epoch's initial state — committed when the epoch began, so it is only available while it is still
+      // the last committed one (simulated_context.rs:102-108; committed states leave `pending`, :163-166)
+      if (prev == 0) return d.f[F_LC_ROUND] == m.ld(L.einit_base + epoch_of(d));
+      return d.f[F_LC_ROUND] == d.gb + prev || is_pend(d, prev);
+    }
     if (d.f[F_LC_ROUND] == prev) return true;
     if (prev == 0) return false;
     return is_pend(d, prev);
@@ -811,7 +832,7 @@ struct Core {
   // Record::Block — verify :263-291, insert :466-476
   LBFT_HD void insert_block(NodeRegs& d, uint32_t r) {
     if (has_blk(d, r)) return;  // "Block was already inserted."
-    uint32_t prev = chain_prev(r);
+    uint32_t prev = chain_prev(d.gb + r);
     if (prev != 0 && !has_qc(d, prev)) return;  // "The previous QC (if any) must be verified first."
     // rounds are increasing by construction (the proposer's hqc round is below its current round)
     if (r == d.f[F_CUR]) d.f[F_FLAGS] |= FL_PROPOSED;  // author == leader(round) by construction (C.1)
@@ -833,14 +854,14 @@ struct Core {
     if (has_qc(d, r)) return;    // "QuorumCertificate was already inserted."
     if (!has_blk(d, r)) return;  // "The certified block hash of a QC must be verified first."
     set_qc(d, r);                // inserted before execution (:505)
-    uint32_t prev = chain_prev(r);
+    uint32_t prev = chain_prev(d.gb + r);
     if (!state_available(d, prev)) return;  // "I failed to execute a block with a QC" — QC stays in the map
     set_pend(d, r, true);
     if (r > d.f[F_HQC]) d.f[F_HQC] = r;
     update_current_round(d, r + 1);
     // update_commit_3chain_round :221-235
     if (prev != 0 && r == prev + 1 && prev - 1 > d.f[F_HCR]) {
-      uint32_t r1 = chain_prev(prev);
+      uint32_t r1 = chain_prev(d.gb + prev);
       if (r1 != 0 && prev == r1 + 1) {
         d.f[F_HCR] = r1;
         d.f[F_HCC] = r;
@@ -875,12 +896,12 @@ struct Core {
     // leader(r) proposes at round r, it does so only while FL_PROPOSED is clear, and that flag is only cleared when
     // the node's round advances.  The explicit per-round "created" bitset is therefore a debug check (host harness).
 #ifdef LBFT_CHECK_C1
-    if (mbit_test(L.created_base, r)) status |= ST_INVARIANT;
-    mbit_set(L.created_base, r);
+    if (mbit_test(L.created_base, d.gb + r)) status |= ST_INVARIANT;
+    mbit_set(L.created_base, d.gb + r);
 #endif
-    m.st(L.chain_base + 2 * r, prev_round | (idx << 16));
-    m.st(L.chain_base + 2 * r + 1, (uint32_t)clk);
-    chain_cache_put(r, prev_round);
+    m.st(L.chain_base + 2 * (d.gb + r), prev_round | (idx << 16));
+    m.st(L.chain_base + 2 * (d.gb + r) + 1, (uint32_t)clk);
+    chain_cache_put(d.gb + r, prev_round);
     insert_block(d, r);
   }
   // create_vote :676-700
@@ -898,18 +919,56 @@ struct Core {
     while (top > after) {
       uint32_t q = top;
       for (;;) {
-        uint32_t p = chain_prev(q);
+        uint32_t p = chain_prev(d.gb + q);
         if (p <= after) break;
         q = p;
       }
       if (!is_pend(d, q)) status |= ST_INVARIANT;  // "Committed states should be known"
       set_pend(d, q, false);
-      if (chain_prev(q) != d.f[F_LC_ROUND]) status |= ST_INVARIANT;  // happened_just_before
-      d.f[F_LC_ROUND] = q;
+      if (chain_parent(d.gb + q) != d.f[F_LC_ROUND]) status |= ST_INVARIANT;  // happened_just_before
+      d.f[F_LC_ROUND] = d.gb + q;
       d.f[F_COMMITS]++;
-      if (d.f[F_COMMITS] >= P.commands_per_epoch) status |= ST_EPOCH_CHANGE;  // read_epoch_id would change
       after = q;
+      // "check if the current epoch just ended" (node.rs:327-347): read_epoch_id = executed commands / commands_per_epoch
+      // (simulated_context.rs:199-207)
+      if (d.f[F_COMMITS] / P.commands_per_epoch > epoch_of(d)) {
+        status |= ST_EPOCH_CHANGE;  // advisory: an epoch change happened in this instance
+        if (!multi()) { status |= ST_ROUND_OVERFLOW; break; }  // the host sized the tables for one epoch: cannot happen
+        switch_epoch(d, d.f[F_COMMITS] / P.commands_per_epoch);
+        break;  // "stop delivering commits after an epoch change"
+      }
     }
+  }
+  // node.rs:329-345: a fresh RecordStoreState for the new epoch (record_store.rs:169-198), initial state = the state just
+  // committed; voting constraints reset.  past_record_stores only serves handle_request, which the simulator answers on
+  // the requester itself (simulator.rs:446) with records the requester already has — nothing to keep.  The pacemaker and
+  // the commit tracker notice the new epoch at their next update (pacemaker.rs:158, node.rs:372-376).
+  LBFT_HD void switch_epoch(NodeRegs& d, uint32_t ne) {
+    if (ne >= L.epochs) { status |= ST_ROUND_OVERFLOW; return; }
+    const uint32_t init = d.f[F_LC_ROUND];
+    const uint32_t seen = m.ld(L.einit_base + ne);
+    if (seen != 0 && seen != init) status |= ST_INVARIANT;  // every node ends an epoch on the same block (App. C.3)
+    m.st(L.einit_base + ne, init);
+    store_bitset_window(d);
+    d.f[F_FLAGS] = (d.f[F_FLAGS] & ~((FL_EPOCH_BITS << FL_EPOCH_SHIFT) | FL_PROPOSED | FL_ELECTION_MASK | FL_HAS_TC)) | (ne << FL_EPOCH_SHIFT);
+    d.gb = ne * L.rspan;
+    d.f[F_CUR] = 1;
+    d.f[F_HQC] = d.f[F_HTC] = d.f[F_HCR] = d.f[F_HCC] = 0;
+    d.f[F_LVR] = d.f[F_LOCKED] = 0;
+    d.f[F_BALLOT] = d.f[F_TOW] = d.f[F_TC_ROUND] = 0;
+    d.vmask = d.tmask = d.tcmask = 0;
+    // the register window of the three bitsets moves to the new epoch's rounds
+    d.cw = (d.gb + 1) >> 5;
+    win = d.cw;
+    d.chb = d.nb[(L.n_hasblk + d.cw) * S];
+    d.chq = d.nb[(L.n_hasqc + d.cw) * S];
+    d.cpd = d.nb[(L.n_pend + d.cw) * S];
+  }
+  LBFT_HD void store_bitset_window(NodeRegs& d) const {
+    if (d.dirty & 1) d.nb[(L.n_hasblk + d.cw) * S] = d.chb;
+    if (d.dirty & 2) d.nb[(L.n_hasqc + d.cw) * S] = d.chq;
+    if (d.dirty & 4) d.nb[(L.n_pend + d.cw) * S] = d.cpd;
+    d.dirty = 0;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -923,7 +982,16 @@ struct Core {
     a.query_all = false;
     // ---- Pacemaker::update_pacemaker, pacemaker.rs:142-207
     uint32_t active = (d.f[F_HQC] > d.f[F_HTC] ? d.f[F_HQC] : d.f[F_HTC]) + 1;
-    if (active > d.f[F_PMR]) {
+    // "epoch_id > self.active_epoch || (epoch_id == self.active_epoch && active_round > self.active_round)", pacemaker.rs:158
+    bool new_epoch = false;
+    if (multi()) {
+      const uint32_t e = epoch_of(d), pe = (d.f[F_FLAGS] >> FL_PM_EPOCH_SHIFT) & FL_EPOCH_BITS;
+      if (e > pe) {
+        new_epoch = true;
+        d.f[F_FLAGS] = (d.f[F_FLAGS] & ~(FL_EPOCH_BITS << FL_PM_EPOCH_SHIFT)) | (e << FL_PM_EPOCH_SHIFT);
+      }
+    }
+    if (new_epoch || active > d.f[F_PMR]) {
       d.f[F_PMR] = active;
       d.f[F_PM_START] = (uint32_t)clk;
       uint32_t ld = P.leader[active];
@@ -969,10 +1037,10 @@ struct Core {
     if (d.f[F_CUR] == d.f[F_PMR] && (d.f[F_FLAGS] & FL_PROPOSED)) {
       uint32_t r = d.f[F_CUR];
       if (r > d.f[F_LVR]) {
-        uint32_t prev = chain_prev(r);  // previous_round(), record_store.rs:588-598
+        uint32_t prev = chain_prev(d.gb + r);  // previous_round(), record_store.rs:588-598
         if (prev >= d.f[F_LOCKED]) {
           d.f[F_LVR] = r;
-          uint32_t sp = prev ? chain_prev(prev) : 0;  // second_previous_round(), :600-609
+          uint32_t sp = prev ? chain_prev(d.gb + prev) : 0;  // second_previous_round(), :600-609
           if (sp > d.f[F_LOCKED]) d.f[F_LOCKED] = sp;
           if (create_vote(d, n, r, prev)) a.send_to = (int32_t)leader;
         }
@@ -985,8 +1053,8 @@ struct Core {
         set_election(d, 2);
         // likewise at most one QC per round: the election is Closed until the round advances (debug check only)
 #ifdef LBFT_CHECK_C1
-        if (mbit_test(L.qcmade_base, r)) status |= ST_INVARIANT;
-        mbit_set(L.qcmade_base, r);
+        if (mbit_test(L.qcmade_base, d.gb + r)) status |= ST_INVARIANT;
+        mbit_set(L.qcmade_base, d.gb + r);
 #endif
         insert_qc(d, r);
         a.broadcast = true;
@@ -995,7 +1063,15 @@ struct Core {
     }
     process_commits(d);
     // ---- CommitTracker::update_tracker, node.rs:364-396
-    if (d.f[F_HCR] > d.f[F_TRK_HCR]) {
+    bool trk_new_epoch = false;
+    if (multi()) {  // "if current_epoch_id > self.epoch_id", node.rs:372-376
+      const uint32_t e = epoch_of(d), te = (d.f[F_FLAGS] >> FL_TRK_EPOCH_SHIFT) & FL_EPOCH_BITS;
+      if (e > te) {
+        trk_new_epoch = true;
+        d.f[F_FLAGS] = (d.f[F_FLAGS] & ~(FL_EPOCH_BITS << FL_TRK_EPOCH_SHIFT)) | (e << FL_TRK_EPOCH_SHIFT);
+      }
+    }
+    if (trk_new_epoch || d.f[F_HCR] > d.f[F_TRK_HCR]) {
       d.f[F_TRK_HCR] = d.f[F_HCR];
       d.f[F_TRK_TIME] = (uint32_t)clk;
     }
@@ -1033,9 +1109,16 @@ struct Core {
     bool has_tc = d.f[F_FLAGS] & FL_HAS_TC;
     uint32_t vote = (uint32_t)((d.vmask >> n) & 1);  // current_vote(author), record_store.rs:762-764
     uint32_t prop = (d.f[F_CUR] == d.f[F_PMR] && (d.f[F_FLAGS] & FL_PROPOSED) && leader_of(d) == n) ? 1u : 0u;
+    uint32_t ep = 0;
+    if (multi()) {
+      // proposed_block(pacemaker) is None while the pacemaker still lives in the previous epoch (record_store.rs:611-615):
+      // the notification built right after an epoch change carries no proposal
+      ep = epoch_of(d);
+      if (((d.f[F_FLAGS] >> FL_PM_EPOCH_SHIFT) & FL_EPOCH_BITS) != ep) prop = 0;
+    }
     pb[0] = d.f[F_HCC] | (d.f[F_HQC] << 16);
     pb[1 * S] = d.f[F_CUR] | ((has_tc ? d.f[F_TC_ROUND] : 0u) << 16);
-    pb[2 * S] = refs | ((vote | (prop << 1)) << 16);
+    pb[2 * S] = refs | ((vote | (prop << 1)) << 16) | (ep << 18);  // [2] refcount:16 | vote | proposal | current_epoch:5
     st_mask(pb + L.p_tcmask * S, has_tc ? d.tcmask : (mask_t)0);
     st_mask(pb + L.p_curmask * S, d.tmask);
     // receivers read a timeout's highest_certified_block_round only for authors in the masks
@@ -1061,6 +1144,16 @@ struct Core {
     uint32_t hcc = w0 & 0xffffu, hqc = w0 >> 16, cur_s = w1 & 0xffffu, tc_round = w1 >> 16;
     bool vote = (w2 >> 16) & 1, prop = (w2 >> 17) & 1;
     bool should_sync = false;
+    if (multi()) {
+      // Every record of a notification belongs to the sender's current epoch (data_sync.rs:82-111; quirk B.9.iii makes the
+      // "previous epoch" commit certificate the current store's).  insert_network_record drops records of another epoch
+      // (node.rs:150-167); a sender that is ahead makes the receiver sync (data_sync.rs:123, 131-134, 143-146).
+      const uint32_t se = (w2 >> 18) & FL_EPOCH_BITS, e = epoch_of(d);
+      if (se != e) {
+        pay_unref(slot, w2);
+        return se > e;
+      }
+    }
     // the two certificates, in message order: highest commit certificate, highest QC (one code copy)
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {
@@ -1159,6 +1252,8 @@ struct Core {
       for (uint32_t w = wl; w < (L.cal_times + 7) / 8; w += G) m.st(L.cal_kmask + w, 0);
     for (uint32_t w = wl; w < N * L.node_words; w += G) m.st(L.node_base + w, 0);
     for (uint32_t w = wl; w < 2 * L.rset_words; w += G) m.st(L.created_base + w, 0);
+    if (multi())
+      for (uint32_t w = wl; w < L.epochs; w += G) m.st(L.einit_base + w, 0);
     grp_sync();
     // EXTENSION D.3: partition plan from a separate stream; must match oracle_capi.cpp make_partition_plan
     if (L.part_windows) {
@@ -1214,7 +1309,13 @@ struct Core {
       // the previous pop, so at most one switch is pending.
       if (REC && rs_pend) {
         const uint32_t rn = rs_pend >> 16, rr = rs_pend & 0xffffu;
-        if (rr <= L.round_cap) m.st(rs_table_base(L) + rn * (L.round_cap + 1) + rr, (uint32_t)t + 1u);
+        // slot [node][0] holds DataWriter::max_round_per_node (round 0 itself is never recorded: 0 > 0 is false): after an
+        // epoch change the active round restarts at 1 and only rounds beyond the recorded maximum count (data_writer.rs:43-46)
+        const uint32_t row = rs_table_base(L) + rn * (L.round_cap + 1);
+        if (rr <= L.round_cap && rr > m.ld(row)) {
+          m.st(row + rr, (uint32_t)t + 1u);
+          m.st(row, rr);
+        }
         rs_pend = 0;
       }
       if (t > clock) clock = t;
@@ -1383,17 +1484,17 @@ struct Core {
       // lay the chain out in commit order in the (now dead) event queue area, then hash it:
       // SimulatedLedgerState::key, simulated_context.rs:51-55
       uint32_t depth = 0;
-      for (uint32_t r = lc; r != 0; r = chain_prev(r)) depth++;
+      for (uint32_t r = lc; r != 0; r = chain_parent(r)) depth++;
       if (depth != commits) status |= ST_INVARIANT;
       uint32_t i = depth;
-      for (uint32_t r = lc; r != 0 && i > 0; r = chain_prev(r)) m.st(scratch + (--i), r);
+      for (uint32_t r = lc; r != 0 && i > 0; r = chain_parent(r)) m.st(scratch + (--i), r);
       SipWords h;
       h.write_u64(depth);
       for (uint32_t k = 0; k < depth; k++) {
         uint32_t r = m.ld(scratch + k);
         uint32_t c0 = m.ld(L.chain_base + 2 * r);
         int32_t tm = (int32_t)m.ld(L.chain_base + 2 * r + 1);
-        h.write_u64(P.leader[r]);
+        h.write_u64(P.leader[multi() ? r % L.rspan : r]);
         h.write_u64(c0 >> 16);
         h.write_u64((uint64_t)(int64_t)tm);
       }

@@ -34,9 +34,11 @@ enum NodeField : uint32_t {
   F_LQA,           // node.latest_query_all_time
   F_TRK_HCR,       // tracker.highest_committed_round
   F_TRK_TIME,      // tracker.latest_commit_time
-  F_FLAGS,         // bit0 current_proposed_block.is_some, bits1-2 election, bit3 has TC, bits8-15 active_leader (0xff None)
+  F_FLAGS,         // bit0 current_proposed_block.is_some, bits1-2 election, bit3 has TC, bits8-15 active_leader (0xff None),
+                   // bits16-20 node.epoch_id, bits21-25 pacemaker.active_epoch, bits26-30 tracker.epoch_id (all 0 unless the
+                   // configuration can reach an epoch change, Layout::epochs > 1)
   F_NEXT_CMD,      // context.next_fetched_command_index
-  F_LC_ROUND,      // round of the block whose state is last_committed_ledger_state (0 = genesis)
+  F_LC_ROUND,      // block whose state is last_committed_ledger_state, as a GLOBAL round id epoch * rspan + round (0 = genesis)
   F_COMMITS,       // committed_history().len()
   F_BALLOT,        // weight of votes for the (single) block of the current round
   F_TOW,           // current_timeouts_weight
@@ -50,7 +52,12 @@ enum : uint32_t {
   FL_ELECTION_MASK = 3u << 1,
   FL_HAS_TC = 1u << 3,
   FL_LEADER_SHIFT = 8,
-  FL_LEADER_NONE = 0xffu
+  FL_LEADER_NONE = 0xffu,
+  FL_EPOCH_SHIFT = 16,      // node.epoch_id (node.rs:32)
+  FL_PM_EPOCH_SHIFT = 21,   // pacemaker.active_epoch (pacemaker.rs:60)
+  FL_TRK_EPOCH_SHIFT = 26,  // tracker.epoch_id (node.rs:354)
+  FL_EPOCH_BITS = 31u,
+  MAX_EPOCHS = 32
 };
 
 struct Layout {
@@ -70,6 +77,12 @@ struct Layout {
   // payload slot: [0] hcc | hqc<<16  [1] cur_round | tc_round<<16  [2] refcount | flags<<16 (bit0 vote, bit1 proposal)
   //               [3..] tc mask, cur mask, tc hcbr[], cur hcbr[]
   uint32_t p_tcmask, p_curmask, p_tchcbr, p_curhcbr;
+  // Epochs (node.rs:329-348).  A record is identified by (epoch, round): its GLOBAL round id is epoch * rspan + round, and
+  // the per-round tables (chain, the three bitsets of a node) cover round_cap = epochs * rspan global ids.  epochs == 1
+  // (commands_per_epoch cannot be reached within the horizon — every BASELINE configuration): rspan == round_cap and
+  // nothing changes.  einit_base: per-instance table [epochs] of the global id of the block whose state is the epoch's
+  // initial state (0 for epoch 0).
+  uint32_t rspan, epochs, einit_base;
 };
 
 #if defined(__CUDACC__)
@@ -84,8 +97,11 @@ struct Layout {
 constexpr uint32_t RES_REG_WORDS = 40;
 
 LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
-                          uint32_t queue_scan, uint32_t max_clock = 0, bool record_rs = false, bool resumable = false) {
+                          uint32_t queue_scan, uint32_t max_clock = 0, bool record_rs = false, bool resumable = false, uint32_t epochs = 1) {
   Layout L{};
+  L.epochs = epochs;
+  L.rspan = round_cap;       // rounds representable per epoch
+  round_cap *= epochs;       // global round ids
   L.queue_scan = queue_scan;
   L.num_nodes = N;
   L.mask_words = N > 32 ? 2 : 1;
@@ -133,6 +149,9 @@ LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue
   if (record_rs) o += N * (round_cap + 1);
   // Resumable runs (LBFT_FLAG_RESUMABLE): a per-instance save area after that table, see res_area_words() below.
   if (resumable) o += RES_REG_WORDS + round_cap + (queue_scan == 2 ? queue_cap + (queue_cap + 1) / 2 : 0);
+  // (appended last so that single-epoch layouts keep every other offset)
+  L.einit_base = o;
+  if (epochs > 1) o += epochs;
   L.total_words = o;
   return L;
 }

@@ -38,7 +38,7 @@ static size_t read_round_switches(const Layout& L, const std::vector<uint32_t>& 
   const uint32_t row = L.round_cap + 1, tile = instance >> 5, lane = instance & 31;
   size_t k = 0;
   for (uint32_t node = 0; node < num_nodes; node++)
-    for (uint32_t r = 0; r < row; r++) {
+    for (uint32_t r = 1; r < row; r++) {  // slot 0 is the per-node maximum, not a switch
       const uint32_t w = state[((size_t)tile * L.total_words + rs_table_base(L) + (size_t)node * row + r) * 32 + lane];
       if (!w) continue;
       if (k < cap) out[k] = lbft_round_switch{node, r, (int64_t)(w - 1u)};
