@@ -82,6 +82,8 @@ struct HostSetup {
   std::string error;
   uint32_t tile_stride = 32;  // instances per state tile (lane interleaving); 1 for the warp-per-instance kernel
   bool use_wide = false;      // launch lbft_wide_kernel (one warp per instance) instead of one thread per instance
+  bool wide_smem = false;     // ... with the instance state in shared memory (committees of <= 16, short horizons)
+  uint32_t wide_group = 32;   // ... lanes per instance: 8 / 16 / 32
 
   bool build(const lbft_config& c) {
     if (c.struct_size != sizeof(lbft_config)) return fail("lbft_config.struct_size does not match this library (ABI mismatch)");
@@ -140,6 +142,25 @@ struct HostSetup {
     // (explicit capacities beyond what the scan queue can encode / scan efficiently select the heap.)
     uint32_t qscan = (N <= 5 && c.max_clock < (1 << 24) - 64) ? 1u : 0u;
     if (c.payload_cap > 255 || c.queue_cap > 512) qscan = 0;
+    // Kernel family.  One thread per instance needs tens of thousands of instances to fill a B200 (65 536 x 4 authors is
+    // exactly one wave of warps) and serialises the 32 instances of a warp through every fan-out; one WARP per instance
+    // (lbft_wide_kernel) has no cross-instance divergence, splits fan-outs, queue scans and per-author vectors over its
+    // lanes, and for committees of <= 16 keeps the whole instance in shared memory.  Measured cross-over (profiles/README.md,
+    // round 2): committees of <= 5 switch below ~4 K instances, larger ones always profit.  Recording / resumable handles
+    // stay on the thread kernel (the wide one has no save area).  LBFT_FORCE_KERNEL=wide|thread overrides (A/B runs).
+    const bool modes = (c.flags & (LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE)) != 0;
+    use_wide = !modes && (N >= 6 || c.num_instances <= 4096);
+    if (const char* f = std::getenv("LBFT_FORCE_KERNEL")) {
+      if (!strcmp(f, "wide") && !modes) use_wide = true;
+      if (!strcmp(f, "thread")) use_wide = false;
+    }
+    tile_stride = use_wide ? 1u : 32u;
+    // lanes per instance: enough for the committee's fan-out, few enough that a warp carries several instances
+    wide_group = N <= 8 ? 8u : (N <= 16 ? 16u : 32u);
+    if (const char* g = std::getenv("LBFT_WIDE_GROUP")) {
+      const int v = atoi(g);
+      if (v == 8 || v == 16 || v == 32) wide_group = (uint32_t)v;
+    }
     // (recording round switches queues the duplicate timers the normal path elides — measured high-water marks
     // roughly double, 46 -> 64+ at N = 4 — so the smallest committees get 128 entries and the HBM scan queue)
     // (resumable runs queue them too: the event dropped at a stop must be the one the reference drops)
@@ -157,6 +178,16 @@ struct HostSetup {
     const double events_per_ms = 0.14 * N * N * (10.0 / (mean_delay < 1.0 ? 1.0 : mean_delay));
     if (qscan && c.max_clock < (1 << 14) - 64 && qcap <= 64 && pcap <= 255 && events_per_ms * (double)c.max_clock < 32768.0)
       qscan = 2;
+    // The wide kernel scans its (single) shared-memory queue with all 32 lanes, so the same compact entries serve committees
+    // up to 16 (4-bit sender/receiver) and queues up to 1 024 entries.
+    if (use_wide && N <= 16 && c.max_clock < (1 << 14) - 64 && pcap <= 255 && events_per_ms * (double)c.max_clock < 32768.0) {
+      const uint32_t want = c.queue_cap ? c.queue_cap : (N <= 4 ? 64u : 8 * N * N);
+      if (want <= 1024) {
+        qscan = 2;
+        qcap = want;
+        if (2 * qcap < rcap) qcap = (rcap + 1) / 2;
+      }
+    }
     // everything else with a moderate horizon: calendar queue (O(1) push/pop, exact: FIFO order inside a (time, kind)
     // list is creation-stamp order); the binary heap remains for long horizons
     if (qscan == 0 && c.max_clock <= 4095 && qcap <= 0xfff0u) qscan = 3;
@@ -176,21 +207,16 @@ struct HostSetup {
       while (epochs > 2 && (uint64_t)epochs * rcap > 32768) epochs--;
       if (qcap < (epochs * rcap + 1) / 2 && qscan) qcap = (epochs * rcap + 1) / 2;  // read-out scratch (see above)
       if (qcap < epochs * rcap && !qscan) qcap = pow2_ceil(epochs * rcap);
-      if (qscan == 2 && qcap > 64) qscan = 1;
+      if (qscan == 2 && qcap > (use_wide ? 1024u : 64u)) qscan = N <= 5 ? 1u : (c.max_clock <= 4095 ? 3u : 0u);
     }
     p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0, epochs);
-    // One thread per instance needs tens of thousands of instances to fill a B200 (65 536 x 4 authors is exactly one wave of
-    // warps) and serialises the 32 instances of a warp through every fan-out; one WARP per instance (lbft_wide_kernel) has
-    // no cross-instance divergence and splits fan-outs, queue scans and per-author vectors over its lanes.  Measured
-    // cross-over (profiles/README.md, round 2): small committees switch at ~16 K instances, committees of 6 and more
-    // always profit.  Recording / resumable handles stay on the thread kernel (the wide one has no save area).
-    // LBFT_FORCE_KERNEL=wide|thread overrides the choice (A/B measurements).
-    use_wide = !record && (N >= 6 || c.num_instances <= 16384);
-    if (const char* f = std::getenv("LBFT_FORCE_KERNEL")) {
-      if (!strcmp(f, "wide") && !record) use_wide = true;
-      if (!strcmp(f, "thread")) use_wide = false;
+    // wide kernel: the whole instance lives in shared memory when four 128-thread blocks (128 / group instances each) of it
+    // fit on an SM
+    {
+      const size_t bytes = sizeof(uint32_t) * (size_t)p.L.total_words + 6u * (size_t)qcap + 1024u;
+      wide_smem = use_wide && qscan == 2 && bytes * (128u / wide_group) <= 56u * 1024u;
+      if (const char* f = std::getenv("LBFT_WIDE_SMEM")) wide_smem = wide_smem && atoi(f) != 0;
     }
-    tile_stride = use_wide ? 1u : 32u;
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)
     leader.resize(rcap + 1);
     for (uint32_t r = 0; r <= rcap; r++) leader[r] = (uint8_t)pick_author(weights, total, siphash13_u64(r));

@@ -4,16 +4,16 @@ namespace lbft {
 cudaError_t launch_wide(const KernelSel& k, const Params& P, cudaStream_t stream) {
   if (!k.wide || k.fixed || k.rec || k.res) return cudaErrorInvalidValue;
   switch (k.qmode) {
-    case 2: return launch_wide_variant<16, 2>(P, stream);
-    case 1: return launch_wide_variant<16, 1>(P, stream);
+    case 2: return k.smem ? launch_wide_groups<16, 2, true>(k, P, stream) : launch_wide_groups<16, 2, false>(k, P, stream);
+    case 1: return launch_wide_groups<16, 1, false>(k, P, stream);
     case 3:
-      if (k.nmax == 16) return launch_wide_variant<16, 3>(P, stream);
-      if (k.nmax == 32) return launch_wide_variant<32, 3>(P, stream);
-      return launch_wide_variant<64, 3>(P, stream);
+      if (k.nmax == 16) return launch_wide_groups<16, 3, false>(k, P, stream);
+      if (k.nmax == 32) return launch_wide_groups<32, 3, false>(k, P, stream);
+      return launch_wide_groups<64, 3, false>(k, P, stream);
     default:
-      if (k.nmax == 16) return launch_wide_variant<16, 0>(P, stream);
-      if (k.nmax == 32) return launch_wide_variant<32, 0>(P, stream);
-      return launch_wide_variant<64, 0>(P, stream);
+      if (k.nmax == 16) return launch_wide_groups<16, 0, false>(k, P, stream);
+      if (k.nmax == 32) return launch_wide_groups<32, 0, false>(k, P, stream);
+      return launch_wide_groups<64, 0, false>(k, P, stream);
   }
 }
 }  // namespace lbft

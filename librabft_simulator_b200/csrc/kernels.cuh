@@ -62,41 +62,62 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
   if (RES) core.save_regs();
 }
 
-// ---- warp per instance -----------------------------------------------------------------------------------------
-// kWideWarps warps per block, each on its own instance (instance = global warp index; the hardware block scheduler hands
+// ---- a group of G lanes per instance ("wide") ---------------------------------------------------------------------
+// kWideWarps warps per block, 32 / G instances per warp (instance = global group index; the hardware block scheduler hands
 // out the next block as soon as one retires, which is the work queue SURVEY §8e asks for).  The state of an instance is one
-// contiguous extent (TileMem<1>: stride 1), tables are read through L1 (every lane reads the same element), the
-// shared-memory queue of QMODE 2 and the fan-out scratch are per warp.
+// contiguous extent (TileMem<1>: stride 1), tables are read through L1 (every lane of a group reads the same element), the
+// shared-memory queue of QMODE 2 and the fan-out scratch are per group.
 constexpr int kWideWarps = 4;
-constexpr int kWideBlocksPerSm = 4;  // 16 warps per SM: <= 128 registers per thread
+#ifndef LBFT_WIDE_BLOCKS
+#define LBFT_WIDE_BLOCKS 4  // blocks per SM the register allocation is bounded for: 4 -> 16 warps per SM, <= 128 registers
+#endif
+constexpr int kWideBlocksPerSm = LBFT_WIDE_BLOCKS;
 
-LBFT_LAYOUT_FN uint32_t wide_smem_words_per_warp(uint32_t queue_cap, int qmode) {
-  const uint32_t scratch = (uint32_t)((sizeof(WideScratch) + 7) / 8 * 2);
-  return scratch + (qmode == 2 ? ((queue_cap + (queue_cap + 1) / 2 + 1) & ~1u) : 0);  // even: the scratch holds doubles
+// Shared memory of one group: [scratch][QMODE 2: queue keys, queue payload halves][SMEM: the instance state]
+LBFT_LAYOUT_FN uint32_t wide_scratch_words() { return (uint32_t)((sizeof(WideScratch) + 7) / 8 * 2); }
+LBFT_LAYOUT_FN uint32_t wide_queue_words(uint32_t queue_cap, int qmode) {
+  return qmode == 2 ? ((queue_cap + (queue_cap + 1) / 2 + 1) & ~1u) : 0u;  // even: what follows holds 64-bit entries
+}
+LBFT_LAYOUT_FN uint32_t wide_smem_words_per_group(const Layout& L, int qmode, bool smem_state) {
+  return wide_scratch_words() + wide_queue_words(L.queue_cap, qmode) + (smem_state ? ((L.total_words + 1) & ~1u) : 0u);
 }
 
-template <int NMAX, int QMODE>
+// SMEM: the instance's state words live in shared memory for the whole run; only the chain table (and the epoch table) is
+// copied to the instance's global extent at the end, for lbft_commit_log / lbft_commit_logs.
+template <int NMAX, int QMODE, bool SMEM, int G>
 __global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(8) uint32_t s_wide[];
-  const uint32_t warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
-  const uint32_t inst = blockIdx.x * kWideWarps + warp;
-  if (inst >= P.num_instances) return;  // whole warps leave together: everything below is warp-uniform
-  uint32_t* base = s_wide + (size_t)warp * wide_smem_words_per_warp(P.L.queue_cap, QMODE);
+  constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
+  const uint32_t grp = threadIdx.x / G, wl = threadIdx.x % G;
+  const uint32_t inst = blockIdx.x * kPerBlock + grp;
+  if (inst >= P.num_instances) return;  // whole groups leave together: everything below is group-uniform
+  uint32_t* base = s_wide + (size_t)grp * wide_smem_words_per_group(P.L, QMODE, SMEM);
   WideScratch* ws = reinterpret_cast<WideScratch*>(base);
-  uint32_t* sk = base + (sizeof(WideScratch) + 7) / 8 * 2;
+  uint32_t* sk = base + wide_scratch_words();
   uint16_t* sd = reinterpret_cast<uint16_t*>(sk + P.L.queue_cap);
-  TileMem<1> mem{P.state + (size_t)inst * P.L.total_words, 0};
-  Core<TileMem<1>, NMAX, QMODE, false, false, false, 32> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
+  uint32_t* gstate = P.state + (size_t)inst * P.L.total_words;
+  uint32_t* state = SMEM ? sk + wide_queue_words(P.L.queue_cap, QMODE) : gstate;
+  TileMem<1> mem{state, 0};
+  Core<TileMem<1>, NMAX, QMODE, false, false, false, G> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
   core.wl = wl;
+  core.gm = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(G - 1)));
   core.ws = ws;
   core.init(P.seeds[inst]);
   core.run();
   core.finalize(inst);
+  if (SMEM) {
+    __syncwarp(core.gm);
+    for (uint32_t w = P.L.chain_base + wl; w < P.L.chain_base + 2 * P.L.round_cap; w += G) gstate[w] = state[w];
+    if (P.L.epochs > 1)
+      for (uint32_t w = wl; w < P.L.epochs; w += G) gstate[P.L.einit_base + w] = state[P.L.einit_base + w];
+  }
 }
 
 // What the host decided to launch for a handle (host_setup.hpp / lbft_api.cu select_kernel).
 struct KernelSel {
   bool wide;   // lbft_wide_kernel instead of lbft_event_loop_kernel
+  bool smem;   // wide kernel: instance state in shared memory
+  int group;   // wide kernel: lanes per instance (8 / 16 / 32)
   int nmax;    // 16 / 32 / 64: width of the author masks
   int qmode;   // Layout::queue_scan
   bool fixed, rec, res;
@@ -122,18 +143,26 @@ inline cudaError_t launch_thread_variants(const KernelSel& k, const Params& P, c
   return cudaGetLastError();
 }
 
-template <int NMAX, int QM>
+template <int NMAX, int QM, bool SMEM, int G>
 inline cudaError_t launch_wide_variant(const Params& P, cudaStream_t stream) {
-  const uint32_t blocks = (P.num_instances + kWideWarps - 1) / kWideWarps;
-  const size_t dyn = (size_t)kWideWarps * wide_smem_words_per_warp(P.L.queue_cap, QM) * sizeof(uint32_t);
-  static bool attr_done = false;  // (one attribute per instantiation; harmless if two threads race)
-  if (!attr_done && dyn > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(lbft_wide_kernel<NMAX, QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
+  const uint32_t blocks = (P.num_instances + kPerBlock - 1) / kPerBlock;
+  const size_t dyn = (size_t)kPerBlock * wide_smem_words_per_group(P.L, QM, SMEM) * sizeof(uint32_t);
+  static size_t attr_set = 48 * 1024;  // (per instantiation; two threads racing set the same or a larger value)
+  if (dyn > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(lbft_wide_kernel<NMAX, QM, SMEM, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_set = dyn;
   }
-  lbft_wide_kernel<NMAX, QM><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
+  lbft_wide_kernel<NMAX, QM, SMEM, G><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
   return cudaGetLastError();
+}
+// the lanes-per-instance dimension of an instantiation family
+template <int NMAX, int QM, bool SMEM>
+inline cudaError_t launch_wide_groups(const KernelSel& k, const Params& P, cudaStream_t stream) {
+  if (k.group == 8) return launch_wide_variant<NMAX, QM, SMEM, 8>(P, stream);
+  if (k.group == 16) return launch_wide_variant<NMAX, QM, SMEM, 16>(P, stream);
+  return launch_wide_variant<NMAX, QM, SMEM, 32>(P, stream);
 }
 
 }  // namespace lbft

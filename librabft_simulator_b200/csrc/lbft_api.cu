@@ -409,6 +409,8 @@ int lbft_run_until(lbft_sim* s, int64_t stop_clock) {
 static KernelSel select_kernel(const lbft_sim* s) {
   KernelSel k{};
   k.wide = s->hs.use_wide;
+  k.smem = s->hs.wide_smem;
+  k.group = (int)s->hs.wide_group;
   k.qmode = (int)s->P.L.queue_scan;
   k.nmax = (k.qmode == 1 || k.qmode == 2) ? 16 : (s->N <= 16 ? 16 : (s->N <= 32 ? 32 : 64));
   k.rec = s->P.record_rs != 0;
@@ -424,7 +426,7 @@ static KernelSel select_kernel(const lbft_sim* s) {
 static std::string kernel_name(const lbft_sim* s) {
   const KernelSel k = select_kernel(s);
   char buf[96];
-  if (k.wide) snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d>", k.nmax, k.qmode);
+  if (k.wide) snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d,%s,%d>", k.nmax, k.qmode, k.smem ? "true" : "false", k.group);
   else
     snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
              k.res ? "true" : "false");

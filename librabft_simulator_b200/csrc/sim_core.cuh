@@ -291,22 +291,24 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // (simulator.rs:383-391: the first event beyond it is popped and dropped), the instance registers are saved to /
 // restored from the save area, and finalize() leaves the queue alone.
 // G: lanes that simulate ONE instance together.  G = 1: one thread per instance, 32 instances per warp (large batches).
-// G = 32 ("wide"): one warp per instance — every lane runs the same scalar state machine on the same values (all
-// branches are warp-uniform, so nothing ever diverges), and the data-parallel pieces (queue scan, per-receiver delay
-// lookup of a fan-out, per-author vectors, table clears) are split over the lanes.  For small batches and large
-// committees, where one thread per instance leaves the machine empty.
+// G = 8 / 16 / 32 ("wide"): a group of G lanes per instance — every lane of the group runs the same scalar state machine
+// on the same values (all branches are group-uniform, so a group never diverges inside), and the data-parallel pieces
+// (queue scan, per-receiver delay lookup of a fan-out, per-author vectors, table clears) are split over its lanes.  A
+// warp holds 32 / G instances; they diverge from each other like the 32 instances of a thread-kernel warp do, only
+// 32 / G ways.  For small batches and large committees, where one thread per instance leaves the machine empty.
 template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, int G = 1>
 struct Core {
   static_assert(!(FIXED && (REC || RES)), "the compile-time layout has neither a round-switch table nor a save area");
-  static_assert(G == 1 || G == 32, "one thread or one warp per instance");
+  static_assert(G == 1 || G == 8 || G == 16 || G == 32, "one thread, or a group of 8 / 16 / 32 lanes per instance");
   static_assert(G == 1 || !(FIXED || REC || RES), "the wide kernel has no fixed-layout / recording / resumable variants");
   static constexpr bool WIDE = G > 1;
   static constexpr int QS = WIDE ? 1 : 32;  // QMODE 2: stride between queue entries in shared memory (a column per lane / contiguous)
   uint32_t wl = 0;            // this thread's lane inside the group (0 when G == 1)
-  WideScratch* ws = nullptr;  // wide kernel: the warp's scratch
-  LBFT_HD static void grp_sync() {
+  uint32_t gm = 0xffffffffu;  // wide kernel: the lanes of this thread's group, as a warp mask
+  WideScratch* ws = nullptr;  // wide kernel: the group's scratch
+  LBFT_HD void grp_sync() const {
 #if defined(__CUDA_ARCH__)
-    if (WIDE) __syncwarp();
+    if (WIDE) __syncwarp(gm);
 #endif
   }
   // Duplicate timers are accounted at push time instead of being queued (push_timer) only when every pop does not
@@ -333,6 +335,8 @@ struct Core {
   uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify, dedup;
   uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
   uint32_t cal_t, cal_free, cal_next;  // QMODE 3: current bucket time, pool free list head, pool bump pointer
+  int32_t part_clock;  // partition plan: the clock part_open was computed for (-1: never)
+  uint64_t part_open;  // ... and the windows open at that clock
   uint32_t rs_pend;  // recording only: node << 16 | active round of the round switch not yet stamped with a pop time (0: none)
   uint32_t cc0, cc1, cc2, cc3;  // chain cache: (round << 16) | previous QC round
 
@@ -630,19 +634,19 @@ struct Core {
     if (QMODE == 2 && WIDE) {
 #if defined(__CUDA_ARCH__)
       // the warp scans its one queue together: lane l looks at entries l, l + 32, ...; keys are unique (creation stamps)
-      __syncwarp();  // entries pushed by this iteration's sends
+      __syncwarp(gm);  // entries pushed by this iteration's sends
       const uint32_t n = qsize;
       uint32_t best = 0xffffffffu, bi = 0;
-      for (uint32_t j = wl; j < n; j += 32) {
+      for (uint32_t j = wl; j < n; j += G) {
         const uint32_t k0 = sk[j];
         if (k0 < best) { best = k0; bi = j; }
       }
-      const uint32_t mn = __reduce_min_sync(0xffffffffu, best);
-      const uint32_t src = (uint32_t)__ffs((int)__ballot_sync(0xffffffffu, best == mn)) - 1u;
-      bi = __shfl_sync(0xffffffffu, bi, (int)src);
+      const uint32_t mn = __reduce_min_sync(gm, best);
+      const uint32_t src = (uint32_t)__ffs((int)__ballot_sync(gm, best == mn)) - 1u;  // a lane of this group (absolute index)
+      bi = __shfl_sync(gm, bi, (int)src);
       const uint32_t lo = sd[bi];
       qsize = n - 1;
-      __syncwarp();  // everyone has read sd[bi] / its share of the keys
+      __syncwarp(gm);  // everyone has read sd[bi] / its share of the keys
       if (bi != n - 1) {
         sk[bi] = sk[n - 1];
         sd[bi] = sd[n - 1];
@@ -685,25 +689,25 @@ struct Core {
     }
     if (QMODE == 1 && WIDE) {
 #if defined(__CUDA_ARCH__)
-      __syncwarp();
+      __syncwarp(gm);
       const uint64_t* q = m.at64(L.heap_time);
       const uint32_t n = qsize;
       uint64_t best = ~0ULL;
       uint32_t bi = 0;
-      for (uint32_t j = wl; j < n; j += 32) {
+      for (uint32_t j = wl; j < n; j += G) {
         const uint64_t k0 = q[(size_t)j * S];
         if (k0 < best) { best = k0; bi = j; }
       }
       // 64-bit minimum over the warp: high words first, then low words among the lanes that hold the minimal high word
-      const uint32_t hi = __reduce_min_sync(0xffffffffu, (uint32_t)(best >> 32));
-      const uint32_t lo32 = __reduce_min_sync(0xffffffffu, (uint32_t)(best >> 32) == hi ? (uint32_t)best : 0xffffffffu);
+      const uint32_t hi = __reduce_min_sync(gm, (uint32_t)(best >> 32));
+      const uint32_t lo32 = __reduce_min_sync(gm, (uint32_t)(best >> 32) == hi ? (uint32_t)best : 0xffffffffu);
       const uint64_t mn = ((uint64_t)hi << 32) | lo32;
-      const uint32_t src = (uint32_t)__ffs((int)__ballot_sync(0xffffffffu, best == mn)) - 1u;
-      bi = __shfl_sync(0xffffffffu, bi, (int)src);
+      const uint32_t src = (uint32_t)__ffs((int)__ballot_sync(gm, best == mn)) - 1u;
+      bi = __shfl_sync(gm, bi, (int)src);
       qsize = n - 1;
       uint64_t* qw = m.at64(L.heap_time);
       const uint64_t last = qw[(size_t)(n - 1) * S];
-      __syncwarp();
+      __syncwarp(gm);
       if (bi != n - 1) qw[(size_t)bi * S] = last;
       time = (int32_t)(mn >> 40);
       kind = 3u - ((uint32_t)(mn >> 38) & 3u);
@@ -1191,11 +1195,21 @@ struct Core {
   // ------------------------------------------------------------------------------------------
   // network sends: schedule_network_event (simulator.rs:266-269) + partition drop (extension)
   // ------------------------------------------------------------------------------------------
-  LBFT_HD bool partitioned(uint32_t a, uint32_t b2) const {  // EXTENSION
-    for (uint32_t k = 0; k < L.part_windows; k++) {
-      int32_t t0 = (int32_t)m.ld(L.part_base + 4 * k), t1 = (int32_t)m.ld(L.part_base + 4 * k + 1);
+  // The windows open at the current clock are found once per clock value (part_clock / part_open: a bit per window),
+  // so a send only looks at the plan while some window is open.
+  LBFT_HD bool partitioned(uint32_t a, uint32_t b2) {  // EXTENSION
+    if (part_clock != clock) {
+      part_clock = clock;
+      part_open = 0;
+      for (uint32_t k = 0; k < L.part_windows; k++) {
+        int32_t t0 = (int32_t)m.ld(L.part_base + 4 * k), t1 = (int32_t)m.ld(L.part_base + 4 * k + 1);
+        if (clock >= t0 && clock < t1) part_open |= 1ULL << k;
+      }
+    }
+    for (uint64_t open = part_open; open; open &= open - 1) {
+      const uint32_t k = ctz64(open);
       uint64_t mask = m.ld(L.part_base + 4 * k + 2) | ((uint64_t)m.ld(L.part_base + 4 * k + 3) << 32);
-      if (clock >= t0 && clock < t1 && (((mask >> a) ^ (mask >> b2)) & 1)) return true;
+      if (((mask >> a) ^ (mask >> b2)) & 1) return true;
     }
     return false;
   }
@@ -1243,6 +1257,7 @@ struct Core {
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
     cal_t = 0; cal_free = PAY_NONE; cal_next = 0;
+    part_clock = -1; part_open = 0;
     if (REC) {
       rs_pend = 0;
       for (uint32_t w = 0; w < N * (L.round_cap + 1); w++) m.st(rs_table_base(L) + w, 0);
@@ -1454,6 +1469,7 @@ struct Core {
   LBFT_HD void restore_regs() {
     const uint32_t b = res_area_base(L, REC);
     uint32_t w = b;
+    part_clock = -1; part_open = 0;  // recomputed at the first send
     uint64_t sx[4];
     for (int i = 0; i < 4; i++) { uint64_t lo = m.ld(w++); uint64_t hi = m.ld(w++); sx[i] = lo | (hi << 32); }
     s0 = sx[0]; s1 = sx[1]; s2 = sx[2]; s3 = sx[3];

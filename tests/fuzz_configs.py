@@ -26,6 +26,8 @@ def random_config(rng):
         kw["partition_max_len"] = int(rng.integers(10, 200))
     max_clock = int(rng.choice([300, 600, 1000, 1500]))
     seed0 = int(rng.integers(1, 1 << 40))
+    if seed0 % 6 == 0:   # epoch changes (node.rs:329-348); derived from seed0 so that the generator's stream is unchanged
+        kw["commands_per_epoch"] = [3, 7, 15, 40][(seed0 // 6) % 4]
     return n, max_clock, seed0, kw
 
 

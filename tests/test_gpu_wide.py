@@ -17,13 +17,16 @@ def test_automatic_choice(monkeypatch):
     picks = {}
     for name, count, nodes, kw in (("config2", 1024, 4, {}), ("config3", 65536, 4, {}), ("config5", 16384, 7, {}),
                                    ("small64", 64, 64, {}), ("resumable", 64, 4, {"resumable": True}),
-                                   ("recording", 64, 7, {"record_round_switches": True})):
-        sim = make_sim(np.arange(1, count + 1, dtype=np.uint64), nodes, **kw).create(1000)
+                                   ("recording", 64, 7, {"record_round_switches": True}), ("mid4", 8192, 4, {}),
+                                   ("long7", 64, 7, {"max_clock": 20000})):
+        max_clock = kw.pop("max_clock", 1000)
+        sim = make_sim(np.arange(1, count + 1, dtype=np.uint64), nodes, **kw).create(max_clock)
         picks[name] = sim.kernel_info()
         sim.close()
-    assert picks["config2"] == "lbft_wide_kernel<16,2>"
-    assert picks["config3"] == "lbft_event_loop_kernel<16,2,true,false,false>"
-    assert picks["config5"] == "lbft_wide_kernel<16,3>" and picks["small64"] == "lbft_wide_kernel<64,3>"
+    assert picks["config2"] == "lbft_wide_kernel<16,2,true>"        # whole instance in shared memory
+    assert picks["config3"] == picks["mid4"] == "lbft_event_loop_kernel<16,2,true,false,false>"
+    assert picks["config5"] == "lbft_wide_kernel<16,2,true>" and picks["small64"] == "lbft_wide_kernel<64,3,false>"
+    assert picks["long7"] == "lbft_wide_kernel<16,0,false>"         # beyond the 14-bit times of the compact queue
     assert picks["resumable"].startswith("lbft_event_loop_kernel") and picks["recording"].startswith("lbft_event_loop_kernel")
 
 
