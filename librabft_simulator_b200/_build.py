@@ -47,6 +47,9 @@ def build_product(force=False, verbose_ptxas=False, extra_flags=(), lib_path=Non
     from concurrent.futures import ThreadPoolExecutor
     lib_path = lib_path or LIB_PATH
     headers = [os.path.join(CSRC, f) for f in PRODUCT_HEADERS] + [os.path.join(ROOT, "include", "lbft.h")]
+    sources = headers + [os.path.join(CSRC, u) for u in PRODUCT_UNITS]
+    if not (force or verbose_ptxas or extra_flags) and _newer(lib_path, sources):
+        return lib_path  # (the objects need not exist: on the GPU box only the library travels)
     objdir = os.path.join(CSRC, "build" if lib_path == LIB_PATH else "build_" + os.path.basename(lib_path))
     os.makedirs(objdir, exist_ok=True)
     jobs = []

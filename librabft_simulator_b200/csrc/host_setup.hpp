@@ -156,10 +156,10 @@ struct HostSetup {
     }
     tile_stride = use_wide ? 1u : 32u;
     // lanes per instance: enough for the committee's fan-out, few enough that a warp carries several instances
-    wide_group = N <= 8 ? 8u : (N <= 16 ? 16u : 32u);
+    wide_group = N <= 8 && c.num_instances > 4096 ? 8u : 32u;
     if (const char* g = std::getenv("LBFT_WIDE_GROUP")) {
       const int v = atoi(g);
-      if (v == 8 || v == 16 || v == 32) wide_group = (uint32_t)v;
+      if (v == 8 || v == 32) wide_group = (uint32_t)v;
     }
     // (recording round switches queues the duplicate timers the normal path elides — measured high-water marks
     // roughly double, 46 -> 64+ at N = 4 — so the smallest committees get 128 entries and the HBM scan queue)
@@ -202,6 +202,7 @@ struct HostSetup {
     // `epochs` spans of round_cap rounds each (global round id = epoch * rspan + round).
     uint32_t epochs = 1;
     if (c.commands_per_epoch < rcap) {
+      wide_group = 32;
       epochs = (uint32_t)(rcap / c.commands_per_epoch) + 2;
       if (epochs > MAX_EPOCHS) epochs = MAX_EPOCHS;
       while (epochs > 2 && (uint64_t)epochs * rcap > 32768) epochs--;
@@ -214,7 +215,7 @@ struct HostSetup {
     // fit on an SM
     {
       const size_t bytes = sizeof(uint32_t) * (size_t)p.L.total_words + 6u * (size_t)qcap + 1024u;
-      wide_smem = use_wide && qscan == 2 && bytes * (128u / wide_group) <= 56u * 1024u;
+      wide_smem = use_wide && qscan == 2 && epochs == 1 && bytes * (128u / wide_group) <= 56u * 1024u;
       if (const char* f = std::getenv("LBFT_WIDE_SMEM")) wide_smem = wide_smem && atoi(f) != 0;
     }
     // leader(round) for every representable round (+1: the pacemaker looks at active_round <= round_cap)

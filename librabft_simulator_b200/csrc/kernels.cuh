@@ -19,13 +19,17 @@ constexpr uint32_t kThrSmem = 256;  // doubles: delay thresholds held in shared 
 // 65 536-instance batch over 148 SMs; <= 144 registers/thread keeps every tile resident).  QMODE 2: two-warp blocks, 7 per
 // SM, so that the ziggurat/threshold tables (6 KB) are shared by two tiles and the per-tile event queues (queue_cap x 32 x
 // 6 B) fit in the 227 KB of shared memory.
+#ifndef LBFT_Q2_WARPS
+#define LBFT_Q2_WARPS 2   // warps per block of the shared-memory-queue kernels (they share the 6 KB of tables)
+#define LBFT_Q2_BLOCKS 7  // ... and blocks per SM: WARPS x BLOCKS = 14 tiles per SM, all 2 048 tiles of the bench batch resident
+#endif
 template <int QMODE>
 struct LaunchShape {
-  static constexpr int kThreads = QMODE == 2 ? 64 : 32;
-  static constexpr int kBlocksPerSm = QMODE == 2 ? 7 : 14;
+  static constexpr int kThreads = QMODE == 2 ? 32 * LBFT_Q2_WARPS : 32;
+  static constexpr int kBlocksPerSm = QMODE == 2 ? LBFT_Q2_BLOCKS : 14;
 };
 
-template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false>
+template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, bool EP = false>
 __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES, 1, EP> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
   if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
   else core.init(P.seeds[inst]);
   core.run();
@@ -84,7 +88,7 @@ LBFT_LAYOUT_FN uint32_t wide_smem_words_per_group(const Layout& L, int qmode, bo
 
 // SMEM: the instance's state words live in shared memory for the whole run; only the chain table (and the epoch table) is
 // copied to the instance's global extent at the end, for lbft_commit_log / lbft_commit_logs.
-template <int NMAX, int QMODE, bool SMEM, int G>
+template <int NMAX, int QMODE, bool SMEM, int G, bool EP = false>
 __global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(8) uint32_t s_wide[];
   constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_k
   uint32_t* gstate = P.state + (size_t)inst * P.L.total_words;
   uint32_t* state = SMEM ? sk + wide_queue_words(P.L.queue_cap, QMODE) : gstate;
   TileMem<1> mem{state, 0};
-  Core<TileMem<1>, NMAX, QMODE, false, false, false, G> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
+  Core<TileMem<1>, NMAX, QMODE, false, false, false, G, EP> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
   core.wl = wl;
   core.gm = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(G - 1)));
   core.ws = ws;
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_k
   if (SMEM) {
     __syncwarp(core.gm);
     for (uint32_t w = P.L.chain_base + wl; w < P.L.chain_base + 2 * P.L.round_cap; w += G) gstate[w] = state[w];
-    if (P.L.epochs > 1)
+    if (EP)
       for (uint32_t w = wl; w < P.L.epochs; w += G) gstate[P.L.einit_base + w] = state[P.L.einit_base + w];
   }
 }
@@ -117,7 +121,8 @@ __global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_k
 struct KernelSel {
   bool wide;   // lbft_wide_kernel instead of lbft_event_loop_kernel
   bool smem;   // wide kernel: instance state in shared memory
-  int group;   // wide kernel: lanes per instance (8 / 16 / 32)
+  int group;   // wide kernel: lanes per instance (8 / 32)
+  bool epochs; // Layout::epochs > 1: the instantiation with the epoch machinery (plain kernels only)
   int nmax;    // 16 / 32 / 64: width of the author masks
   int qmode;   // Layout::queue_scan
   bool fixed, rec, res;
@@ -136,33 +141,39 @@ inline cudaError_t launch_thread_variants(const KernelSel& k, const Params& P, c
   constexpr int T = LaunchShape<QM>::kThreads;
   const uint32_t blocks = (P.num_instances + T - 1) / T;
   const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2) : 0;
-  if (k.rec && k.res) lbft_event_loop_kernel<NMAX, QM, false, true, true><<<blocks, T, dyn, stream>>>(P);
+  if (k.epochs) {
+    if (k.rec || k.res) return cudaErrorInvalidValue;  // (refused at lbft_create)
+    lbft_event_loop_kernel<NMAX, QM, false, false, false, true><<<blocks, T, dyn, stream>>>(P);
+  } else if (k.rec && k.res) lbft_event_loop_kernel<NMAX, QM, false, true, true><<<blocks, T, dyn, stream>>>(P);
   else if (k.res) lbft_event_loop_kernel<NMAX, QM, false, false, true><<<blocks, T, dyn, stream>>>(P);
   else if (k.rec) lbft_event_loop_kernel<NMAX, QM, false, true><<<blocks, T, dyn, stream>>>(P);
   else lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, stream>>>(P);
   return cudaGetLastError();
 }
 
-template <int NMAX, int QM, bool SMEM, int G>
+template <int NMAX, int QM, bool SMEM, int G, bool EP>
 inline cudaError_t launch_wide_variant(const Params& P, cudaStream_t stream) {
   constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
   const uint32_t blocks = (P.num_instances + kPerBlock - 1) / kPerBlock;
   const size_t dyn = (size_t)kPerBlock * wide_smem_words_per_group(P.L, QM, SMEM) * sizeof(uint32_t);
   static size_t attr_set = 48 * 1024;  // (per instantiation; two threads racing set the same or a larger value)
   if (dyn > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lbft_wide_kernel<NMAX, QM, SMEM, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaError_t e = cudaFuncSetAttribute(lbft_wide_kernel<NMAX, QM, SMEM, G, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     attr_set = dyn;
   }
-  lbft_wide_kernel<NMAX, QM, SMEM, G><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
+  lbft_wide_kernel<NMAX, QM, SMEM, G, EP><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
   return cudaGetLastError();
 }
-// the lanes-per-instance dimension of an instantiation family
+// the lanes-per-instance / epoch dimensions of an instantiation family (the host only selects these combinations)
 template <int NMAX, int QM, bool SMEM>
 inline cudaError_t launch_wide_groups(const KernelSel& k, const Params& P, cudaStream_t stream) {
-  if (k.group == 8) return launch_wide_variant<NMAX, QM, SMEM, 8>(P, stream);
-  if (k.group == 16) return launch_wide_variant<NMAX, QM, SMEM, 16>(P, stream);
-  return launch_wide_variant<NMAX, QM, SMEM, 32>(P, stream);
+  if (k.epochs) {
+    if (SMEM || k.group != 32) return cudaErrorInvalidValue;
+    return launch_wide_variant<NMAX, QM, false, 32, true>(P, stream);
+  }
+  if (k.group == 8) return launch_wide_variant<NMAX, QM, SMEM, 8, false>(P, stream);
+  return launch_wide_variant<NMAX, QM, SMEM, 32, false>(P, stream);
 }
 
 }  // namespace lbft

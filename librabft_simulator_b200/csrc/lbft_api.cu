@@ -215,6 +215,11 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
     delete s;
     return set_error(LBFT_ERR_INVALID, e);
   }
+  if (s->hs.params.L.epochs > 1 && (s->hs.params.record_rs || s->hs.params.resumable)) {
+    delete s;
+    return set_error(LBFT_ERR_INVALID, "recording / resumable handles need commands_per_epoch >= round_cap: the kernels with the epoch "
+                                       "machinery (node.rs:329-348) are built for plain runs only");
+  }
   s->I = config->num_instances;
   s->N = config->num_nodes;
   s->device = config->device;
@@ -411,6 +416,7 @@ static KernelSel select_kernel(const lbft_sim* s) {
   k.wide = s->hs.use_wide;
   k.smem = s->hs.wide_smem;
   k.group = (int)s->hs.wide_group;
+  k.epochs = s->P.L.epochs > 1;
   k.qmode = (int)s->P.L.queue_scan;
   k.nmax = (k.qmode == 1 || k.qmode == 2) ? 16 : (s->N <= 16 ? 16 : (s->N <= 32 ? 32 : 64));
   k.rec = s->P.record_rs != 0;
@@ -426,10 +432,11 @@ static KernelSel select_kernel(const lbft_sim* s) {
 static std::string kernel_name(const lbft_sim* s) {
   const KernelSel k = select_kernel(s);
   char buf[96];
-  if (k.wide) snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d,%s,%d>", k.nmax, k.qmode, k.smem ? "true" : "false", k.group);
+  if (k.wide)
+    snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d,%s,%d,%s>", k.nmax, k.qmode, k.smem ? "true" : "false", k.group, k.epochs ? "true" : "false");
   else
-    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
-             k.res ? "true" : "false");
+    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s,%s>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
+             k.res ? "true" : "false", k.epochs ? "true" : "false");
   return buf;
 }
 

@@ -296,8 +296,12 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // (queue scan, per-receiver delay lookup of a fan-out, per-author vectors, table clears) are split over its lanes.  A
 // warp holds 32 / G instances; they diverge from each other like the 32 instances of a thread-kernel warp do, only
 // 32 / G ways.  For small batches and large committees, where one thread per instance leaves the machine empty.
-template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, int G = 1>
+// EP: the configuration can reach an epoch change (Layout::epochs > 1; node.rs:329-348).  A template parameter because the
+// machinery (global round ids, per-epoch record-store reset, epoch fields of pacemaker / tracker / notification) costs ~20 %
+// of the code and the instructions of a generic kernel when it is a run-time test, and no BASELINE configuration needs it.
+template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, int G = 1, bool EP = false>
 struct Core {
+  static_assert(!(FIXED && EP), "the compile-time layout is single-epoch");
   static_assert(!(FIXED && (REC || RES)), "the compile-time layout has neither a round-switch table nor a save area");
   static_assert(G == 1 || G == 8 || G == 16 || G == 32, "one thread, or a group of 8 / 16 / 32 lanes per instance");
   static_assert(G == 1 || !(FIXED || REC || RES), "the wide kernel has no fixed-layout / recording / resumable variants");
@@ -447,7 +451,7 @@ struct Core {
     return m.ld(L.chain_base + 2 * g) & 0xffffu;
   }
   // Epochs (node.rs:329-348): only configurations whose commands_per_epoch can be reached carry the machinery.
-  LBFT_HD bool multi() const { return !FIXED && L.epochs > 1; }
+  LBFT_HD static constexpr bool multi() { return EP; }
   // GLOBAL id of the block whose state block g was executed on: its previous QC's block, or the epoch's initial state.
   LBFT_HD uint32_t chain_parent(uint32_t g) const {
     const uint32_t p = chain_prev(g);
@@ -935,7 +939,7 @@ struct Core {
       after = q;
       // "check if the current epoch just ended" (node.rs:327-347): read_epoch_id = executed commands / commands_per_epoch
       // (simulated_context.rs:199-207)
-      if (d.f[F_COMMITS] / P.commands_per_epoch > epoch_of(d)) {
+      if (multi() ? d.f[F_COMMITS] / P.commands_per_epoch > epoch_of(d) : d.f[F_COMMITS] >= P.commands_per_epoch) {
         status |= ST_EPOCH_CHANGE;  // advisory: an epoch change happened in this instance
         if (!multi()) { status |= ST_ROUND_OVERFLOW; break; }  // the host sized the tables for one epoch: cannot happen
         switch_epoch(d, d.f[F_COMMITS] / P.commands_per_epoch);

@@ -33,3 +33,13 @@ def test_known_outcome(oracle):
     sim, g = gpu_run(seeds, 4, 1000, commands_per_epoch=10)
     assert_same(oracle.run(seeds, 4, 1000, commands_per_epoch=10), g)
     assert g.commit_counts.max() <= 12 and (g.status & 32).all()          # was [34, 34, 34, 34] behind an error flag in round 1
+
+
+def test_epochs_with_modes_are_refused_on_the_device():
+    """The kernels with the epoch machinery are built for plain runs only (recording / resumable x epochs is covered on the
+    host-compiled core, tests/test_epochs.py)."""
+    from librabft_simulator_b200 import _lib
+    from tests.test_gpu_parity import make_sim
+    with pytest.raises(_lib.LbftError) as e:
+        make_sim([1, 2], 4, commands_per_epoch=10, resumable=True).create(1000)
+    assert e.value.code == -1 and "epoch" in str(e.value)

@@ -9,12 +9,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "librabft_simulator_b200", "csrc")
 work = [w.split(":") for w in sys.argv[1:]] or [("2", "1024"), ("5", "16384"), ("4", "2048"), ("1", "1")]
-libs = [("r128", "liblbft_b200.so"), ("r85", "liblbft_b200_w6.so"), ("r64", "liblbft_b200_w8.so")]
+libs = [("r128", "liblbft_b200.so")]
 for cid, inst in work:
     for lname, lib in libs:
         if not os.path.exists(os.path.join(CSRC, lib)):
             continue
-        for group in ("8", "16", "32"):
+        for group in ("8", "32"):
             for smem in ("0", "1"):
                 env = dict(os.environ, LBFT_LIB_PATH=os.path.join(CSRC, lib), LBFT_WIDE_GROUP=group, LBFT_WIDE_SMEM=smem, LBFT_FORCE_KERNEL="wide")
                 p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "profile_one.py"), cid, inst, "wide", "3"], env=env,
