@@ -156,7 +156,10 @@ struct HostSetup {
     }
     tile_stride = use_wide ? 1u : 32u;
     // lanes per instance: enough for the committee's fan-out, few enough that a warp carries several instances
-    wide_group = N <= 8 && c.num_instances > 4096 ? 8u : 32u;
+    // (measured, profiles/README.md r2e: 8 lanes per instance — four instances per warp — win once the batch fills the machine
+    // with warps, committees of 64 included: 8 192 x 64 takes 1.14 s against 1.63 s with a warp per instance; below ~4 K
+    // instances a whole warp per instance has the lower latency)
+    wide_group = c.num_instances > 4096 ? 8u : 32u;
     if (const char* g = std::getenv("LBFT_WIDE_GROUP")) {
       const int v = atoi(g);
       if (v == 8 || v == 32) wide_group = (uint32_t)v;

@@ -152,6 +152,8 @@ LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue
   // (appended last so that single-epoch layouts keep every other offset)
   L.einit_base = o;
   if (epochs > 1) o += epochs;
+  o = (o + 1) & ~1u;  // an instance is a whole number of 8-byte units: with one instance per extent (wide kernel, stride 1) the
+                      // 64-bit queue entries of every instance stay aligned
   L.total_words = o;
   return L;
 }

@@ -37,6 +37,30 @@ static void run_all(const Params& P, std::vector<uint32_t>& state, const double*
   else run_all_ep<NMAX, QMODE, REC, RES, false>(P, state, zx, zf);
 }
 
+// The bench kernel's instantiation (compile-time layout + draw ring, sim_core.cuh FIXED / RING) on the host: selected exactly
+// as lbft_api.cu select_kernel does, so that the default four-author configurations of the CPU tests exercise the ring.
+static void run_all_fixed(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
+  for (uint32_t inst = 0; inst < P.num_instances; inst++) {
+    uint32_t tile = inst / 32, lane = inst % 32;
+    TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
+    std::vector<uint32_t> sk((size_t)P.L.queue_cap * 32), rlo(8 * 32), rhi(8 * 32);
+    std::vector<uint16_t> sd((size_t)P.L.queue_cap * 32), rdl(8 * 32);
+    Core<TileMem<32>, 16, 2, true> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
+    core.rlo = rlo.data() + lane;
+    core.rhi = rhi.data() + lane;
+    core.rdl = rdl.data() + lane;
+    core.init(P.seeds[inst]);
+    core.run();
+    core.finalize(inst);
+  }
+}
+static bool fixed_selected(const Params& P) {
+  constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
+  const bool plain_model = P.delay_kind == LBFT_DELAY_LOGNORMAL && !P.delay_const && P.delay_kmax != 0 && P.delay_kmax + 2 <= 256 &&
+                           P.silent_mask == 0;
+  return P.L.queue_scan == 2 && plain_model && !P.record_rs && !P.resumable && memcmp(&P.L, &kFixed, sizeof(Layout)) == 0;
+}
+
 static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
                     uint32_t* counters, uint32_t* status, uint32_t* words_per_instance, std::vector<uint32_t>& state,
                     Params& P, const int64_t* stops = nullptr, size_t nstops = 0);
@@ -154,7 +178,8 @@ static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* las
                               : run_all<NMAX, QS, false, true>(P, state, P.zig_x, P.zig_f))                          \
                : (P.record_rs ? run_all<NMAX, QS, true, false>(P, state, P.zig_x, P.zig_f)                          \
                               : run_all<NMAX, QS, false, false>(P, state, P.zig_x, P.zig_f)))
-  if (P.L.queue_scan == 2) RUN(16, 2);
+  if (fixed_selected(P) && !getenv("HOSTCORE_NO_FIXED")) run_all_fixed(P, state, P.zig_x, P.zig_f);
+  else if (P.L.queue_scan == 2) RUN(16, 2);
   else if (P.L.queue_scan == 1) RUN(16, 1);
   else if (P.L.queue_scan == 3) {
     if (c->num_nodes <= 16) RUN(16, 3);
