@@ -198,8 +198,10 @@ def oracle_seconds_per_instance(cfg, threads):
     """Probe: wall seconds per instance with `threads` threads busy (one instance per task)."""
     n = min(cfg["instances"], 2 * threads)
     _, dt, _ = run_cpu_sample(cfg, step_seeds(cfg, 4000, 0, n), threads)   # also warms the thread pool / page cache
-    if dt < 0.2:  # too short to extrapolate from: take a sample that runs for a noticeable time
-        n = min(cfg["instances"], max(n, int(n * 0.5 / max(dt, 1e-4))))
+    for _ in range(2):  # too short to extrapolate from (start-up costs, scheduler noise): grow the sample to about a second
+        if dt >= 0.5 or n >= cfg["instances"]:
+            break
+        n = min(cfg["instances"], max(2 * n, int(n * 1.0 / max(dt, 1e-4))))
         _, dt, _ = run_cpu_sample(cfg, step_seeds(cfg, 4100, 0, n), threads)
     return dt / n
 

@@ -4,15 +4,8 @@
 namespace lbft {
 cudaError_t launch_fixed(const KernelSel& k, const Params& P, cudaStream_t stream) {
   if (k.wide || !k.fixed || k.qmode != 2) return cudaErrorInvalidValue;
-  constexpr int T = LaunchShape<2, true>::kThreads;
-  const size_t dyn = (size_t)(T / 32) * q2_tile_words(64, true) * sizeof(uint32_t);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(lbft_event_loop_kernel<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  lbft_event_loop_kernel<16, 2, true><<<(P.num_instances + T - 1) / T, T, dyn, stream>>>(P);
+  constexpr int T = LaunchShape<2>::kThreads;
+  lbft_event_loop_kernel<16, 2, true><<<(P.num_instances + T - 1) / T, T, (size_t)(T / 32) * 64 * (32 * 4 + 32 * 2), stream>>>(P);
   return cudaGetLastError();
 }
 }  // namespace lbft

@@ -23,20 +23,14 @@ constexpr uint32_t kThrSmem = 256;  // doubles: delay thresholds held in shared 
 #define LBFT_Q2_WARPS 2   // warps per block of the shared-memory-queue kernels (they share the 6 KB of tables)
 #define LBFT_Q2_BLOCKS 7  // ... and blocks per SM: WARPS x BLOCKS = 14 tiles per SM, all 2 048 tiles of the bench batch resident
 #endif
-#ifndef LBFT_FIXED_WARPS
-#define LBFT_FIXED_WARPS 7   // the bench kernel: seven-warp blocks, two per SM (14 tiles per SM again) — the tables are shared by
-#define LBFT_FIXED_BLOCKS 2  // seven tiles instead of two, which makes room for the draw rings (sim_core.cuh RING) in shared memory
-#endif
-template <int QMODE, bool FIXED = false>
+template <int QMODE>
 struct LaunchShape {
-  static constexpr int kThreads = FIXED ? 32 * LBFT_FIXED_WARPS : (QMODE == 2 ? 32 * LBFT_Q2_WARPS : 32);
-  static constexpr int kBlocksPerSm = FIXED ? LBFT_FIXED_BLOCKS : (QMODE == 2 ? LBFT_Q2_BLOCKS : 14);
+  static constexpr int kThreads = QMODE == 2 ? 32 * LBFT_Q2_WARPS : 32;
+  static constexpr int kBlocksPerSm = QMODE == 2 ? LBFT_Q2_BLOCKS : 14;
 };
-// shared memory of one tile (warp) of the QMODE 2 kernels: queue keys + payload halves, and for the bench kernel the draw ring
-LBFT_LAYOUT_FN uint32_t q2_tile_words(uint32_t queue_cap, bool ring) { return queue_cap * 32 + queue_cap * 16 + (ring ? 8u * (32 + 32 + 16) : 0u); }
 
 template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, bool EP = false>
-__global__ void __launch_bounds__(LaunchShape<QMODE, FIXED>::kThreads, LaunchShape<QMODE, FIXED>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
   // measured 1.5x slower for the whole kernel (44.1 vs 28.9 ms).
@@ -60,17 +54,11 @@ __global__ void __launch_bounds__(LaunchShape<QMODE, FIXED>::kThreads, LaunchSha
   uint16_t* sd = nullptr;
   if (QMODE == 2) {
     const uint32_t warp = threadIdx.x >> 5, qcap = P.L.queue_cap;
-    uint32_t* base = s_queue + (size_t)warp * q2_tile_words(qcap, FIXED);  // keys (qcap*32 words) + payload (qcap*32 halves) [+ ring]
+    uint32_t* base = s_queue + (size_t)warp * (qcap * 32 + qcap * 16);  // keys (qcap*32 words) + payload (qcap*32 halves)
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
   Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES, 1, EP> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
-  if (FIXED) {  // the draw ring: 8 entries x (lo, hi, delay) columns per lane, behind the tile's queue
-    uint32_t* ring = s_queue + (size_t)(threadIdx.x >> 5) * q2_tile_words(P.L.queue_cap, true) + P.L.queue_cap * 48;
-    core.rlo = ring + lane;
-    core.rhi = ring + 8 * 32 + lane;
-    core.rdl = reinterpret_cast<uint16_t*>(ring + 16 * 32) + lane;
-  }
   if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
   else core.init(P.seeds[inst]);
   core.run();

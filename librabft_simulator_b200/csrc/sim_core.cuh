@@ -365,62 +365,7 @@ struct Core {
   }
   LBFT_HD uint64_t next_u64() {
     draws++;
-    if (RING && rcount) {
-      uint32_t dl;
-      return ring_pop(dl);
-    }
     return xoshiro_next(s0, s1, s2, s3);
-  }
-  // ---- the draw ring (bench kernel) ---------------------------------------------------------------------------------
-  // The instance's RNG stream is sequential, but WHO needs the next draw — a delay, a shuffle step, nobody — differs from
-  // lane to lane and from event to event, so the generator and the delay lookup used to run with ~5 of 32 lanes active
-  // (20 % of the kernel's instructions).  Each lane now keeps the next kRing raw draws of its stream in shared memory,
-  // together with what the draw is worth as a network delay when it passes the ziggurat's fast test (98.8 %); the warp
-  // tops the rings up together at the head of the event loop whenever some lane runs low, at full lane occupancy.
-  // Consumers take draws in stream order, so nothing observable changes: `draws` counts consumption, a draw used by a
-  // shuffle simply ignores the precomputed delay, and the rare slow path of the ziggurat rewinds the generator to the
-  // consumed position (xoshiro256** is invertible) and carries on sequentially.
-  static constexpr bool RING = FIXED;
-  static constexpr uint32_t kRing = 8, kRingLow = 2;
-  uint32_t* rlo = nullptr;  // this lane's columns: rlo[j * 32], rhi[j * 32] = raw draw j, rdl[j * 32] = its delay or 0xffff
-  uint32_t* rhi = nullptr;
-  uint16_t* rdl = nullptr;
-  uint32_t rhead = 0, rcount = 0;
-  LBFT_HD uint64_t ring_pop(uint32_t& dl) {
-    const uint32_t j = rhead;
-    const uint64_t v = (uint64_t)rlo[j * 32] | ((uint64_t)rhi[j * 32] << 32);
-    dl = rdl[j * 32];
-    rhead = (j + 1) & (kRing - 1);
-    rcount--;
-    return v;
-  }
-  // One step backwards of xoshiro256** (the inverse of xoshiro_next's state transition).
-  LBFT_HD void xoshiro_prev() {
-    const uint64_t b3 = (s3 >> 45) | (s3 << 19);  // a3 ^ a1
-    const uint64_t a0 = s0 ^ b3;
-    const uint64_t c = s1 ^ s2;                   // a1 ^ (a1 << 17)
-    const uint64_t a1 = c ^ (c << 17) ^ (c << 34) ^ (c << 51);
-    const uint64_t a2 = s1 ^ a1 ^ a0;
-    const uint64_t a3 = b3 ^ a1;
-    s0 = a0; s1 = a1; s2 = a2; s3 = a3;
-  }
-  // Forget the ring: the generator goes back to the position of the next unconsumed draw.
-  LBFT_HD void ring_flush() {
-    for (; rcount; rcount--) xoshiro_prev();
-    rhead = 0;
-  }
-  LBFT_HD void ring_refill() {
-    while (rcount < kRing) {
-      const uint64_t bits = xoshiro_next(s0, s1, s2, s3);
-      const uint32_t i = (uint32_t)bits & 0xffu;
-      const double u = bits_to_f64((1024ULL << 52) | (bits >> 12)) - 3.0;
-      const double x = mul_rn(u, zx[i]);
-      const uint32_t j = (rhead + rcount) & (kRing - 1);
-      rlo[j * 32] = (uint32_t)bits;
-      rhi[j * 32] = (uint32_t)(bits >> 32);
-      rdl[j * 32] = fabs(x) < zx[i + 1] ? (uint16_t)delay_from_z(x) : (uint16_t)0xffffu;
-      rcount++;
-    }
   }
   LBFT_HD uint32_t gen_range_u32(uint32_t n) {  // UniformInt<u32>::sample_single_inclusive(0, n-1)
     uint32_t zone = (n << clz32(n)) - 1;
@@ -438,15 +383,14 @@ struct Core {
       if (lo <= zone) return mulhi64(v, n);
     }
   }
-  LBFT_HD double standard_normal() { return standard_normal_from(next_u64()); }
-  LBFT_HD double standard_normal_from(uint64_t bits) {  // rand_distr ziggurat, 256 layers; `bits` = the first draw
-    for (;; bits = next_u64()) {
+  LBFT_HD double standard_normal() {  // rand_distr ziggurat, 256 layers
+    for (;;) {
+      uint64_t bits = next_u64();
       uint32_t i = (uint32_t)bits & 0xffu;
       double u = bits_to_f64((1024ULL << 52) | (bits >> 12)) - 3.0;
       double xi = zx[i], xi1 = zx[i + 1];
       double x = mul_rn(u, xi);
       if (fabs(x) < xi1) return x;  // ~98.8 % of the draws
-      if (RING) ring_flush();  // the out-of-line path works on the generator itself: bring it back to the consumed position
       NormalSlow o = normal_slow(s0, s1, s2, s3, draws, i, u, x, zf[i], zf[i + 1], P.zig_r);
       s0 = o.s0; s1 = o.s1; s2 = o.s2; s3 = o.s3;
       draws = o.draws;
@@ -466,13 +410,6 @@ struct Core {
   // GlobalTime::add_delay (simulator.rs:110-118): returns the delay in ms.
   LBFT_HD int32_t sample_delay() {
     if (!FIXED && P.delay_kind == 1u) return (int32_t)(P.uni_lo + gen_range_u64(P.uni_span));
-    if (RING && rcount) {
-      uint32_t dl;
-      const uint64_t bits = ring_pop(dl);
-      draws++;
-      if (dl != 0xffffu) return (int32_t)dl;               // the delay was worked out when the ring was filled
-      return delay_from_z(standard_normal_from(bits));      // fast test failed: wedge / tail, sequentially
-    }
     double z = standard_normal();
     if (!FIXED && P.delay_const) return (int32_t)P.delay_const_value;  // sigma == 0: exp(mu) evaluated by the host libm
     if (FIXED || P.delay_kmax) return delay_from_z(z);
@@ -1375,14 +1312,6 @@ struct Core {
     const uint32_t N = L.num_nodes;
 #pragma unroll 1
     while (qsize > 0 && !(status & ST_FATAL)) {
-      if (RING) {
-        // top the draw rings up together, at full lane occupancy, whenever some lane of the warp runs low
-#if defined(__CUDA_ARCH__)
-        if (__any_sync(__activemask(), rcount <= kRingLow)) ring_refill();
-#else
-        if (rcount <= kRingLow) ring_refill();
-#endif
-      }
       int32_t t;
       uint32_t kind, data;
       pop_event(t, kind, data);

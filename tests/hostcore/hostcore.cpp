@@ -37,18 +37,15 @@ static void run_all(const Params& P, std::vector<uint32_t>& state, const double*
   else run_all_ep<NMAX, QMODE, REC, RES, false>(P, state, zx, zf);
 }
 
-// The bench kernel's instantiation (compile-time layout + draw ring, sim_core.cuh FIXED / RING) on the host: selected exactly
-// as lbft_api.cu select_kernel does, so that the default four-author configurations of the CPU tests exercise the ring.
+// The bench kernel's instantiation (compile-time layout, sim_core.cuh FIXED) on the host: selected exactly as lbft_api.cu
+// select_kernel does, so that the default four-author configurations of the CPU tests exercise the very code the bench runs.
 static void run_all_fixed(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
-    std::vector<uint32_t> sk((size_t)P.L.queue_cap * 32), rlo(8 * 32), rhi(8 * 32);
-    std::vector<uint16_t> sd((size_t)P.L.queue_cap * 32), rdl(8 * 32);
+    std::vector<uint32_t> sk((size_t)P.L.queue_cap * 32);
+    std::vector<uint16_t> sd((size_t)P.L.queue_cap * 32);
     Core<TileMem<32>, 16, 2, true> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
-    core.rlo = rlo.data() + lane;
-    core.rhi = rhi.data() + lane;
-    core.rdl = rdl.data() + lane;
     core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);

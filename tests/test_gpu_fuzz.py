@@ -45,6 +45,7 @@ def test_fuzz_modes_gpu_vs_oracle(oracle):
     rng = np.random.default_rng(20260923)
     for _ in range(60):
         n, max_clock, seed0, kw = random_config(rng)
+        kw.pop("commands_per_epoch", None)   # epochs x recording / staged runs: host-compiled core only (tests/test_epochs.py)
         flags, stops = random_modes(rng, max_clock)
         check_modes(oracle, run, switches, n, max_clock, seed0, kw, flags, stops, count=12)
     for old in live.values():
