@@ -116,7 +116,7 @@ typedef struct lbft_config {
   double delay_variance;
   int64_t delay_lo, delay_hi;     /* LBFT_DELAY_UNIFORM only                                           */
   int64_t target_commit_interval; /* NodeConfig, node.rs:76-81                                         */
-  int64_t delta;
+  int64_t delta;                  /* > 0 (delta = 0 is refused: SURVEY App. C.1b)                      */
   double gamma;
   double lambda;
   uint64_t commands_per_epoch;    /* SimulatedContext::new(_, _, max_command_per_epoch)                */

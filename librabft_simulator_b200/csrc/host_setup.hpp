@@ -94,6 +94,10 @@ struct HostSetup {
     if (c.flags & ~(uint32_t)(LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE)) return fail("unknown bits in flags");
     if (c.commands_per_epoch == 0) return fail("commands_per_epoch must be > 0");
     if (c.delta < 0 || c.target_commit_interval < 0) return fail("delta and target_commit_interval must be >= 0");
+    // delta == 0 makes round durations 0: a node can then create a timeout and propose in the same update (SURVEY App.
+    // C.1b), which the round-id form does not represent (the device would flag every instance LBFT_ST_INVARIANT after
+    // running the whole batch).  Refuse it up front.
+    if (c.delta == 0) return fail("delta = 0 is not supported: a timeout and a proposal in the same update (SURVEY App. C.1b)");
     const uint32_t N = c.num_nodes;
     Params& p = params;
     p.num_instances = c.num_instances;
@@ -181,6 +185,9 @@ struct HostSetup {
     const double events_per_ms = 0.14 * N * N * (10.0 / (mean_delay < 1.0 ? 1.0 : mean_delay));
     if (qscan && c.max_clock < (1 << 14) - 64 && qcap <= 64 && pcap <= 255 && events_per_ms * (double)c.max_clock < 32768.0)
       qscan = 2;
+    // the HBM scan queue hands out 22-bit creation stamps: long horizons / very short delays go to the heap or calendar
+    // queue (30-bit / 32-bit stamps) instead of aborting with LBFT_ST_QUEUE_OVERFLOW half-way through
+    if (qscan == 1 && events_per_ms * (double)c.max_clock > 2.0e6) qscan = 0;
     // The wide kernel scans its (single) shared-memory queue with all 32 lanes, so the same compact entries serve committees
     // up to 16 (4-bit sender/receiver) and queues up to 1 024 entries.
     if (use_wide && N <= 16 && c.max_clock < (1 << 14) - 64 && pcap <= 255 && events_per_ms * (double)c.max_clock < 32768.0) {

@@ -186,9 +186,10 @@ static int finish_download(lbft_sim* s, int set) {
   if (*r.error & LBFT_ST_ERROR_MASK) {
     for (size_t i = 0; i < I; i++)
       if (r.status[i] & LBFT_ST_ERROR_MASK) {
-        char buf[200];
-        snprintf(buf, sizeof buf, "instance %zu ended with status 0x%x (see lbft_status; raise round_cap/queue_cap/payload_cap)", i,
-                 r.status[i]);
+        char buf[360];
+        snprintf(buf, sizeof buf, "instance %zu ended with status 0x%x (see lbft_status; raise round_cap/queue_cap/payload_cap%s)", i,
+                 r.status[i], (r.status[i] & LBFT_ST_QUEUE_OVERFLOW) ? "; QUEUE_OVERFLOW also means the queue mode ran out of creation "
+                 "stamps: queue_cap > 512 selects a queue with wider stamps" : "");
         return set_error(LBFT_ERR_CAPACITY, buf);
       }
   }
