@@ -84,6 +84,7 @@ pub mod ffi {
     pub const LBFT_ERR_CAPACITY: c_int = -4;
     pub const LBFT_FLAG_ROUND_SWITCHES: u32 = 1;
     pub const LBFT_FLAG_RESUMABLE: u32 = 2;
+    pub const LBFT_FLAG_TRUE_DATA_SYNC: u32 = 4;
 
     pub enum LbftSim {}
 

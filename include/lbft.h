@@ -77,6 +77,11 @@ typedef struct lbft_round_switch {
 /* lbft_config.flags */
 #define LBFT_FLAG_ROUND_SWITCHES 1u /* record round switches = loop_until(.., Some(csv_path)) simulator.rs:380-381 */
 #define LBFT_FLAG_RESUMABLE 2u      /* lbft_run_until / snapshots: loop_until may be called again with a larger clock   */
+/* NON-PARITY variant: a data-sync request is answered by the node it was SENT TO, from that node's records, and the requester
+ * inserts the records of the response (what librabft-v2/src/data_sync.rs:183-240 is written for).  The reference simulator
+ * dispatches the request to the requester itself (bft-lib/src/simulator.rs:446), which makes every round trip a no-op; that
+ * behaviour is the default here, as its golden tests pin it.  Plain runs only (no other flag, commands_per_epoch >= round_cap). */
+#define LBFT_FLAG_TRUE_DATA_SYNC 4u
 
 /* Per-instance event counters (simulator.rs:31 event_count; data_writer.rs message counter). */
 typedef struct lbft_instance_counters {

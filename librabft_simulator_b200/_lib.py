@@ -35,6 +35,7 @@ class LbftRoundSwitch(ctypes.Structure):
 
 FLAG_ROUND_SWITCHES = 1  # LBFT_FLAG_ROUND_SWITCHES
 FLAG_RESUMABLE = 2  # LBFT_FLAG_RESUMABLE
+FLAG_TRUE_DATA_SYNC = 4  # LBFT_FLAG_TRUE_DATA_SYNC (non-parity variant)
 
 
 class LbftTiming(ctypes.Structure):

@@ -91,7 +91,10 @@ struct HostSetup {
     if (c.num_nodes < 1 || c.num_nodes > 64) return fail("num_nodes must be in 1..64");
     if (!c.seeds) return fail("seeds must not be NULL");
     if (c.max_clock < 0 || c.max_clock >= (1 << 29)) return fail("max_clock must be in [0, 2^29)");
-    if (c.flags & ~(uint32_t)(LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE)) return fail("unknown bits in flags");
+    if (c.flags & ~(uint32_t)(LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE | LBFT_FLAG_TRUE_DATA_SYNC)) return fail("unknown bits in flags");
+    const bool tds = (c.flags & LBFT_FLAG_TRUE_DATA_SYNC) != 0;
+    if (tds && (c.flags & (LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE)))
+      return fail("LBFT_FLAG_TRUE_DATA_SYNC cannot be combined with recording / resumable runs");
     if (c.commands_per_epoch == 0) return fail("commands_per_epoch must be > 0");
     if (c.delta < 0 || c.target_commit_interval < 0) return fail("delta and target_commit_interval must be >= 0");
     // delta == 0 makes round durations 0: a node can then create a timeout and propose in the same update (SURVEY App.
@@ -153,9 +156,9 @@ struct HostSetup {
     // round 2): committees of <= 5 switch below ~4 K instances, larger ones always profit.  Recording / resumable handles
     // stay on the thread kernel (the wide one has no save area).  LBFT_FORCE_KERNEL=wide|thread overrides (A/B runs).
     const bool modes = (c.flags & (LBFT_FLAG_ROUND_SWITCHES | LBFT_FLAG_RESUMABLE)) != 0;
-    use_wide = !modes && (N >= 6 || c.num_instances <= 4096);
+    use_wide = !modes && !tds && (N >= 6 || c.num_instances <= 4096);
     if (const char* f = std::getenv("LBFT_FORCE_KERNEL")) {
-      if (!strcmp(f, "wide") && !modes) use_wide = true;
+      if (!strcmp(f, "wide") && !modes && !tds) use_wide = true;
       if (!strcmp(f, "thread")) use_wide = false;
     }
     tile_stride = use_wide ? 1u : 32u;
@@ -177,6 +180,8 @@ struct HostSetup {
     if (qcap < rcap && !qscan) qcap = rcap;
     if (qcap > (1u << 20)) return fail("queue_cap too large");
     uint32_t pcap = c.payload_cap ? c.payload_cap : (N <= 4 ? 32u : (N <= 8 ? 64u : pow2_ceil(8 * N)));
+    // (true data-sync keeps a snapshot per request and per response in flight as well)
+    if (tds && !c.payload_cap) pcap = N <= 4 ? 128u : (N <= 8 ? 192u : 4 * pcap);
     if (pcap > 0xfff0u) return fail("payload_cap must be < 65520");
     // shortest horizons: 32-bit keys (time:14 | kind:2 | stamp:16) + 16-bit payload words, queue in shared memory
     // (16-bit stamps: ~0.14 N^2 events are created per simulated ms at the reference's 10 ms mean delay, and
@@ -212,6 +217,7 @@ struct HostSetup {
     // `epochs` spans of round_cap rounds each (global round id = epoch * rspan + round).
     uint32_t epochs = 1;
     if (c.commands_per_epoch < rcap) {
+      if (tds) return fail("LBFT_FLAG_TRUE_DATA_SYNC needs commands_per_epoch >= round_cap (single-epoch runs)");
       wide_group = 32;
       epochs = (uint32_t)(rcap / c.commands_per_epoch) + 2;
       if (epochs > MAX_EPOCHS) epochs = MAX_EPOCHS;
@@ -220,7 +226,7 @@ struct HostSetup {
       if (qcap < epochs * rcap && !qscan) qcap = pow2_ceil(epochs * rcap);
       if (qscan == 2 && qcap > (use_wide ? 1024u : 64u)) qscan = N <= 5 ? 1u : (c.max_clock <= 4095 ? 3u : 0u);
     }
-    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0, epochs);
+    p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0, epochs, tds);
     // wide kernel: the whole instance lives in shared memory when four 128-thread blocks (128 / group instances each) of it
     // fit on an SM
     {

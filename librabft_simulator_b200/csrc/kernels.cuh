@@ -29,7 +29,7 @@ struct LaunchShape {
   static constexpr int kBlocksPerSm = QMODE == 2 ? LBFT_Q2_BLOCKS : 14;
 };
 
-template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, bool EP = false>
+template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, bool EP = false, bool TDS = false>
 __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES, 1, EP> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES, 1, EP, TDS> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
   if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
   else core.init(P.seeds[inst]);
   core.run();
@@ -123,6 +123,7 @@ struct KernelSel {
   bool smem;   // wide kernel: instance state in shared memory
   int group;   // wide kernel: lanes per instance (8 / 32)
   bool epochs; // Layout::epochs > 1: the instantiation with the epoch machinery (plain kernels only)
+  bool tds;    // LBFT_FLAG_TRUE_DATA_SYNC (plain single-epoch thread kernels only)
   int nmax;    // 16 / 32 / 64: width of the author masks
   int qmode;   // Layout::queue_scan
   bool fixed, rec, res;
@@ -141,7 +142,10 @@ inline cudaError_t launch_thread_variants(const KernelSel& k, const Params& P, c
   constexpr int T = LaunchShape<QM>::kThreads;
   const uint32_t blocks = (P.num_instances + T - 1) / T;
   const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2) : 0;
-  if (k.epochs) {
+  if (k.tds) {
+    if (k.rec || k.res || k.epochs) return cudaErrorInvalidValue;  // (refused at lbft_create)
+    lbft_event_loop_kernel<NMAX, QM, false, false, false, false, true><<<blocks, T, dyn, stream>>>(P);
+  } else if (k.epochs) {
     if (k.rec || k.res) return cudaErrorInvalidValue;  // (refused at lbft_create)
     lbft_event_loop_kernel<NMAX, QM, false, false, false, true><<<blocks, T, dyn, stream>>>(P);
   } else if (k.rec && k.res) lbft_event_loop_kernel<NMAX, QM, false, true, true><<<blocks, T, dyn, stream>>>(P);

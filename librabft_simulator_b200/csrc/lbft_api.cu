@@ -418,6 +418,7 @@ static KernelSel select_kernel(const lbft_sim* s) {
   k.smem = s->hs.wide_smem;
   k.group = (int)s->hs.wide_group;
   k.epochs = s->P.L.epochs > 1;
+  k.tds = s->P.L.tds != 0;
   k.qmode = (int)s->P.L.queue_scan;
   k.nmax = (k.qmode == 1 || k.qmode == 2) ? 16 : (s->N <= 16 ? 16 : (s->N <= 32 ? 32 : 64));
   k.rec = s->P.record_rs != 0;
@@ -426,7 +427,7 @@ static KernelSel select_kernel(const lbft_sim* s) {
   constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
   const bool plain_model = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0 &&
                            s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
-  k.fixed = !k.wide && k.qmode == 2 && plain_model && !k.rec && !k.res && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0;
+  k.fixed = !k.wide && k.qmode == 2 && plain_model && !k.rec && !k.res && !s->P.L.tds && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0;
   return k;
 }
 // ... spelled like the symbol ncu / cuobjdump show.
@@ -436,8 +437,8 @@ static std::string kernel_name(const lbft_sim* s) {
   if (k.wide)
     snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d,%s,%d,%s>", k.nmax, k.qmode, k.smem ? "true" : "false", k.group, k.epochs ? "true" : "false");
   else
-    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s,%s>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
-             k.res ? "true" : "false", k.epochs ? "true" : "false");
+    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s,%s,%s>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
+             k.res ? "true" : "false", k.epochs ? "true" : "false", k.tds ? "true" : "false");
   return buf;
 }
 

@@ -299,9 +299,15 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // EP: the configuration can reach an epoch change (Layout::epochs > 1; node.rs:329-348).  A template parameter because the
 // machinery (global round ids, per-epoch record-store reset, epoch fields of pacemaker / tracker / notification) costs ~20 %
 // of the code and the instructions of a generic kernel when it is a run-time test, and no BASELINE configuration needs it.
-template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, int G = 1, bool EP = false>
+// TDS: LBFT_FLAG_TRUE_DATA_SYNC — a data-sync request is answered by the node it was sent to, from that node's records,
+// and the response's records are inserted by the requester (what data_sync.rs:183-240 is written for), instead of the
+// reference simulator's dispatch to the requester itself (simulator.rs:446).  An opt-in NON-PARITY
+// variant; plain thread-per-instance kernels only.
+template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, int G = 1, bool EP = false,
+          bool TDS = false>
 struct Core {
   static_assert(!(FIXED && EP), "the compile-time layout is single-epoch");
+  static_assert(!(TDS && (FIXED || REC || RES || EP || G > 1)), "true data-sync: plain single-epoch thread kernels only");
   static_assert(!(FIXED && (REC || RES)), "the compile-time layout has neither a round-switch table nor a save area");
   static_assert(G == 1 || G == 8 || G == 16 || G == 32, "one thread, or a group of 8 / 16 / 32 lanes per instance");
   static_assert(G == 1 || !(FIXED || REC || RES), "the wide kernel has no fixed-layout / recording / resumable variants");
@@ -1172,9 +1178,15 @@ struct Core {
       }
     }
     if (prop) insert_block(d, cur_s);
-    // timeouts: the TC's first, then the sender's current ones, ascending author.
-    // A group whose round is not the receiver's current round is rejected wholesale, and accepting
-    // a timeout can only move the receiver's round away from the group's round.
+    insert_timeout_groups(d, pb, tc_round, cur_s, tcm, curm);
+    if (vote) insert_vote(d, cur_s, sender);
+    pay_unref(slot, w2);
+    return should_sync;
+  }
+  // timeouts of a notification / response: the TC's first, then the sender's current ones, ascending author.
+  // A group whose round is not the receiver's current round is rejected wholesale, and accepting
+  // a timeout can only move the receiver's round away from the group's round.
+  LBFT_HD void insert_timeout_groups(NodeRegs& d, const uint32_t* pb, uint32_t tc_round, uint32_t cur_s, mask_t tcm, mask_t curm) {
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {
       uint32_t round = which ? cur_s : tc_round;
@@ -1191,9 +1203,63 @@ struct Core {
         }
       }
     }
-    if (vote) insert_vote(d, cur_s, sender);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // LBFT_FLAG_TRUE_DATA_SYNC (TDS): request / response payloads in round-id form
+  // ------------------------------------------------------------------------------------------
+  // create_request (data_sync.rs:179-181) -> known_quorum_certificate_rounds (record_store.rs:766-799): the rounds at
+  // positions 0, 1, 3, 7, ... of the QC chains that end in the highest QC and in the highest commit certificate.
+  LBFT_HD void write_request_rounds(const NodeRegs& d, uint32_t slot) {
+    uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
+    for (uint32_t w = 0; w < L.rset_words; w++) pb[(L.p_rounds + w) * S] = 0;
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+      uint32_t q = which ? d.f[F_HCC] : d.f[F_HQC];
+      for (uint32_t i = 0; q != 0; i++, q = chain_prev(q))
+        if ((i & (i + 1)) == 0) pb[(L.p_rounds + (q >> 5)) * S] |= 1u << (q & 31);
+    }
+  }
+  // handle_request (data_sync.rs:183-207) on the node `n` the request was sent to -> unknown_records
+  // (record_store.rs:801-831): the QCs (with their blocks) of both chains down to the first round the requester knows,
+  // the timeouts (TC's, then current), the current proposed block; votes are skipped.  A snapshot, like a notification.
+  LBFT_HD void write_response(uint32_t n, const NodeRegs& d, uint32_t req_slot, uint32_t slot) {
+    HcbrRegs hc;
+    prefetch_hcbr(d, hc);
+    write_notification(n, d, slot, 1u, hc);
+    uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
+    const uint32_t* rq = m.at(L.pay_base + req_slot * L.pay_words);
+    pb[0] = 0;  // no certificates of their own: they are in the round set
+    pb[2 * S] = 1u | ((d.f[F_FLAGS] & FL_PROPOSED) ? (1u << 17) : 0u);  // current_proposed_block, whoever proposed it
+    for (uint32_t w = 0; w < L.rset_words; w++) pb[(L.p_rounds + w) * S] = 0;
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
+      uint32_t q = which ? d.f[F_HCC] : d.f[F_HQC];
+      while (q != 0 && !((rq[(L.p_rounds + (q >> 5)) * S] >> (q & 31)) & 1u)) {
+        pb[(L.p_rounds + (q >> 5)) * S] |= 1u << (q & 31);
+        q = chain_prev(q);
+      }
+    }
+  }
+  // handle_response (data_sync.rs:209-240): the records in order — block and QC per round ascending, timeouts, the
+  // proposed block.
+  LBFT_HD void handle_response(NodeRegs& d, uint32_t slot) {
+    uint32_t* pb = m.at(L.pay_base + slot * L.pay_words);
+    const uint32_t w1 = pb[1 * S], w2 = pb[2 * S];
+    const mask_t tcm = ld_mask(pb + L.p_tcmask * S), curm = ld_mask(pb + L.p_curmask * S);
+    const uint32_t cur_s = w1 & 0xffffu, tc_round = w1 >> 16;
+    for (uint32_t w = 0; w < L.rset_words; w++) {
+      uint32_t bits = pb[(L.p_rounds + w) * S];
+      while (bits) {
+        const uint32_t r = w * 32 + ctz32(bits);
+        bits &= bits - 1;
+        insert_block(d, r);
+        insert_qc(d, r);
+      }
+    }
+    insert_timeout_groups(d, pb, tc_round, cur_s, tcm, curm);
+    if ((w2 >> 17) & 1) insert_block(d, cur_s);
     pay_unref(slot, w2);
-    return should_sync;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1348,7 +1414,7 @@ struct Core {
         bool drop = (P.silent_mask >> receiver) & 1;
         if (kind == EV_REQUEST && ((P.silent_mask >> sender) & 1)) drop = true;
         if (drop) {
-          if (kind == EV_NOTIFY) pay_unref(slot, m.ld(L.pay_base + slot * L.pay_words + 2));
+          if (kind == EV_NOTIFY || (TDS && slot != PAY_NONE)) pay_unref(slot, m.ld(L.pay_base + slot * L.pay_words + 2));
           continue;
         }
       }
@@ -1359,7 +1425,9 @@ struct Core {
       a.broadcast = false;
       a.query_all = false;
       bool should_sync = false;
+      uint32_t sync_slot = PAY_NONE;  // TDS: the sync request's payload, written when handle_notification asks for it
       const bool is_request = kind == EV_REQUEST;  // answered by `receiver` itself (simulator.rs:446): no state change
+      if (TDS && is_request) load_node(sender, d);  // ... unless the node it was sent to answers (read only, never stored)
       if (!is_request) {
         load_node(receiver, d);
         const uint32_t pmr_before = d.f[F_PMR];
@@ -1367,7 +1435,14 @@ struct Core {
           cancelled++;
           continue;
         }
-        if (kind == EV_NOTIFY) should_sync = handle_notification(d, slot, sender);
+        if (kind == EV_NOTIFY) {
+          should_sync = handle_notification(d, slot, sender);
+          if (TDS && should_sync) {  // create_request_internal runs inside handle_notification, before the update (data_sync.rs:172-176)
+            sync_slot = pay_alloc();
+            if (sync_slot != PAY_NONE) write_request_rounds(d, sync_slot);
+          }
+        }
+        if (TDS && kind == EV_RESPONSE && slot != PAY_NONE) handle_response(d, slot);
         a = update_node(receiver, d, clock - (int32_t)d.f[F_STARTUP]);
         if (REC && d.f[F_PMR] > pmr_before) rs_pend = (receiver << 16) | (d.f[F_PMR] & 0xffffu);
         // next UpdateTimerEvent, simulator.rs:311-324
@@ -1421,6 +1496,12 @@ struct Core {
           sched_notify += list.len;
           prefetch_hcbr(d, hc);
         }
+        const bool req_payload = TDS && ev_kind == EV_REQUEST, resp_payload = TDS && ev_kind == EV_RESPONSE;
+        if (req_payload) {
+          pslot = phase == 0 ? sync_slot : pay_alloc();
+          if (phase != 0 && pslot != PAY_NONE) write_request_rounds(d, pslot);  // create_request at send time, simulator.rs:365-368
+        }
+        if (resp_payload) pslot = pay_alloc();
         uint32_t queued = 0;
         // Wide kernel, table-served LogNormal delay: the normal deviates of the fan-out are drawn first (the RNG stream is
         // sequential), then each lane turns its share of them into delays, then the events are queued in list order.
@@ -1442,6 +1523,17 @@ struct Core {
         if (to_other && pslot != PAY_NONE) {
           if (queued) write_notification(receiver, d, pslot, queued, hc);
           else pay_release(pslot);
+        }
+        if (req_payload && pslot != PAY_NONE) {
+          if (queued) m.st(L.pay_base + pslot * L.pay_words + 2, queued);  // one reference per queued copy of the request
+          else pay_release(pslot);
+        }
+        if (resp_payload) {
+          if (pslot != PAY_NONE) {
+            if (queued && slot != PAY_NONE) write_response(sender, d, slot, pslot);
+            else pay_release(pslot);
+          }
+          if (slot != PAY_NONE) pay_unref(slot, m.ld(L.pay_base + slot * L.pay_words + 2));  // this copy of the request has been answered
         }
       }
       if (!is_request) store_node(d);

@@ -83,6 +83,9 @@ struct Layout {
   // nothing changes.  einit_base: per-instance table [epochs] of the global id of the block whose state is the epoch's
   // initial state (0 for epoch 0).
   uint32_t rspan, epochs, einit_base;
+  // LBFT_FLAG_TRUE_DATA_SYNC: payload slots carry a per-round bitset behind the notification fields — the requester's
+  // known QC rounds in a request, the rounds whose block + QC the responder hands over in a response.
+  uint32_t p_rounds, tds;
 };
 
 #if defined(__CUDACC__)
@@ -97,7 +100,8 @@ struct Layout {
 constexpr uint32_t RES_REG_WORDS = 40;
 
 LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue_cap, uint32_t payload_cap, uint32_t part_windows,
-                          uint32_t queue_scan, uint32_t max_clock = 0, bool record_rs = false, bool resumable = false, uint32_t epochs = 1) {
+                          uint32_t queue_scan, uint32_t max_clock = 0, bool record_rs = false, bool resumable = false, uint32_t epochs = 1,
+                          bool true_data_sync = false) {
   Layout L{};
   L.epochs = epochs;
   L.rspan = round_cap;       // rounds representable per epoch
@@ -141,6 +145,9 @@ LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue
   L.p_tchcbr = L.p_curmask + L.mask_words;
   L.p_curhcbr = L.p_tchcbr + L.hcbr_words;
   L.pay_words = L.p_curhcbr + L.hcbr_words;
+  L.p_rounds = L.pay_words;
+  L.tds = true_data_sync ? 1u : 0u;
+  if (true_data_sync) L.pay_words += L.rset_words;
   L.pay_base = o; o += payload_cap * L.pay_words;
   // DataWriter round-switch table (data_writer.rs:14), only when recording (LBFT_FLAG_ROUND_SWITCHES): [node][round 0..round_cap]
   // = pop time + 1 (pops are at t >= 1; 0 = never seen), num_nodes * (round_cap + 1) words at the END of the instance, found

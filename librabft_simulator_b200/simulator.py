@@ -145,10 +145,14 @@ class BatchSimulator:
 
     def __init__(self, seeds, num_nodes, network_delay=RandomDelay(), node_config=NodeConfig(),
                  commands_per_epoch=30000, voting_rights=None, silent=None, partition_windows=0,
-                 partition_max_len=0, device=0, round_cap=0, queue_cap=0, payload_cap=0, record_round_switches=False, resumable=False):
+                 partition_max_len=0, device=0, round_cap=0, queue_cap=0, payload_cap=0, record_round_switches=False, resumable=False,
+                 true_data_sync=False):
         self._lib = _lib.load()
         self.record_round_switches = bool(record_round_switches)  # LBFT_FLAG_ROUND_SWITCHES (DataWriter, data_writer.rs)
         self.resumable = bool(resumable)  # LBFT_FLAG_RESUMABLE: run_until / snapshot / restore
+        # LBFT_FLAG_TRUE_DATA_SYNC: NON-PARITY variant — requests are answered by the node they were sent to (the reference
+        # simulator dispatches them to the requester itself, simulator.rs:446)
+        self.true_data_sync = bool(true_data_sync)
         self.seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64).reshape(-1))
         self.num_instances = int(self.seeds.shape[0])
         self.num_nodes = int(num_nodes)
@@ -179,7 +183,8 @@ class BatchSimulator:
         c.silent = None if self.silent is None else self.silent.ctypes.data
         c.partition_windows, c.partition_max_len = self.partition_windows, self.partition_max_len
         c.device, c.round_cap, c.queue_cap, c.payload_cap = self.device, self.round_cap, self.queue_cap, self.payload_cap
-        c.flags = (_lib.FLAG_ROUND_SWITCHES if self.record_round_switches else 0) | (_lib.FLAG_RESUMABLE if self.resumable else 0)
+        c.flags = ((_lib.FLAG_ROUND_SWITCHES if self.record_round_switches else 0) | (_lib.FLAG_RESUMABLE if self.resumable else 0) |
+                   (_lib.FLAG_TRUE_DATA_SYNC if self.true_data_sync else 0))
         return c
 
     def create(self, max_clock):

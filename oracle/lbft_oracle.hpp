@@ -1151,6 +1151,9 @@ struct SimConfig {
     uint64_t side_mask;
   };
   std::vector<PartitionWindow> partitions;
+  // LBFT_FLAG_TRUE_DATA_SYNC (NON-PARITY variant): handle_request runs on the node the request was sent
+  // to instead of on the requester (simulator.rs:446 uses `receiver`)
+  bool true_data_sync = false;
 };
 
 enum EventKind { EV_NOTIFY = 0, EV_REQUEST = 1, EV_RESPONSE = 2, EV_TIMER = 3 };
@@ -1339,8 +1342,9 @@ struct Simulator {
           break;
         }
         case EV_REQUEST: {
-          // QUIRK (simulator.rs:446): the request is answered by `receiver` itself.
-          SimulatedNode& node = nodes[ev.receiver];
+          // QUIRK (simulator.rs:446): the request is answered by `receiver` itself — unless the opt-in variant asks for
+          // the node it was sent to.
+          SimulatedNode& node = nodes[cfg.true_data_sync ? ev.sender : ev.receiver];
           int p = (int)resp_pool.size();
           resp_pool.push_back(node.node.handle_request(req_pool[ev.payload]));
           schedule_network_event(EV_RESPONSE, ev.receiver, ev.sender, p);

@@ -28,6 +28,7 @@ static bool make_cfg(const lbft_config* c, SimConfig& s, std::string& err) {
   s.node.gamma = c->gamma;
   s.node.lambda = c->lambda;
   s.commands_per_epoch = c->commands_per_epoch;
+  s.true_data_sync = (c->flags & LBFT_FLAG_TRUE_DATA_SYNC) != 0;
   if (c->voting_rights) s.voting_rights.assign(c->voting_rights, c->voting_rights + c->num_nodes);
   if (c->silent) s.silent.assign(c->silent, c->silent + c->num_nodes);
   return true;

@@ -12,14 +12,14 @@
 using namespace lbft;
 static thread_local std::string g_err;
 
-template <int NMAX, int QMODE, bool REC, bool RES, bool EP>
+template <int NMAX, int QMODE, bool REC, bool RES, bool EP, bool TDS = false>
 static void run_all_ep(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
     std::vector<uint32_t> sk(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);  // stands in for the shared-memory queue
     std::vector<uint16_t> sd(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);
-    Core<TileMem<32>, NMAX, QMODE, false, REC, RES, 1, EP> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
+    Core<TileMem<32>, NMAX, QMODE, false, REC, RES, 1, EP, TDS> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
     // QMODE 2: the stand-in for the shared-memory queue is per call, like shared memory is per launch
     if (RES && (P.run_flags & 1u)) core.restore_regs();
     else core.init(P.seeds[inst]);
@@ -33,7 +33,9 @@ static void run_all_ep(const Params& P, std::vector<uint32_t>& state, const doub
 // runs; the product library has it for plain kernels only)
 template <int NMAX, int QMODE, bool REC, bool RES>
 static void run_all(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
-  if (P.L.epochs > 1) run_all_ep<NMAX, QMODE, REC, RES, true>(P, state, zx, zf);
+  if (P.L.tds) {
+    if (!REC && !RES) run_all_ep<NMAX, QMODE, false, false, false, true>(P, state, zx, zf);  // (HostSetup refuses the other combinations)
+  } else if (P.L.epochs > 1) run_all_ep<NMAX, QMODE, REC, RES, true>(P, state, zx, zf);
   else run_all_ep<NMAX, QMODE, REC, RES, false>(P, state, zx, zf);
 }
 

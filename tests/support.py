@@ -55,6 +55,7 @@ class LbftRoundSwitch(ctypes.Structure):
 
 FLAG_ROUND_SWITCHES = 1
 FLAG_RESUMABLE = 2
+FLAG_TRUE_DATA_SYNC = 4
 
 
 def _round_switches(fn, err, seeds, num_nodes, instance, max_clock, **kw):

@@ -41,7 +41,7 @@ def test_invalid_configs_are_rejected(lib):
     cfg.struct_size = 12
     assert lib.lbft_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"struct_size" in lib.lbft_last_error()
-    for field, value in (("num_nodes", 0), ("num_nodes", 65), ("max_clock", -1), ("delay_kind", 7), ("flags", 4), ("flags", 0x80000001),
+    for field, value in (("num_nodes", 0), ("num_nodes", 65), ("max_clock", -1), ("delay_kind", 7), ("flags", 8), ("flags", 0x80000001), ("flags", 4 | 2),
                          ("commands_per_epoch", 0), ("delay_mean", -1.0), ("delta", 0)):
         cfg, keep = make_config([1, 2], 4)
         setattr(cfg, field, value)

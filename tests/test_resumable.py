@@ -79,7 +79,7 @@ def test_staged_needs_the_flag_and_a_stop_inside_the_horizon(hostcore):
     with pytest.raises(RuntimeError, match="stop_clock"):
         hostcore.run_staged([1], 4, [500, 1001])
     with pytest.raises(RuntimeError, match="flags"):
-        hostcore.setup_info(4, flags=4)
+        hostcore.setup_info(4, flags=8)
 
 
 def test_save_area_is_appended_after_everything_else(hostcore):

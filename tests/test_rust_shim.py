@@ -109,7 +109,7 @@ def test_extern_functions_match_the_header():
 
 
 def test_flag_constants_and_link_flags():
-    for cname in ("LBFT_FLAG_ROUND_SWITCHES", "LBFT_FLAG_RESUMABLE"):
+    for cname in ("LBFT_FLAG_ROUND_SWITCHES", "LBFT_FLAG_RESUMABLE", "LBFT_FLAG_TRUE_DATA_SYNC"):
         cval = int(re.search(r"#define %s (\d+)u" % cname, HEADER).group(1))
         rval = int(re.search(r"pub const %s: u32 = (\d+);" % cname, RUST).group(1))
         assert cval == rval, cname
