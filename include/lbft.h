@@ -219,7 +219,9 @@ int lbft_snapshot_load(lbft_sim* sim, const void* buf, size_t bytes);
 
 /* Device address of a result buffer, for callers that consume results on the GPU (e.g. an NCCL
  * all-gather of per-instance commit counts): which = 0 commit counts [I][N] u32, 1 last states [I][N]
- * u64, 2 counters [I][12] u32, 3 status [I] u32, 4 active rounds [I] u32.  Valid until lbft_destroy. */
+ * u64, 2 counters [I][12] u32, 3 status [I] u32, 4 active rounds [I] u32, 5 = buffers 1, 0 and 4 as the one contiguous block they are
+ * allocated in (last states, commit counts, active rounds — in this order): the summaries of a shard in a single collective.
+ * Valid until lbft_destroy. */
 int lbft_device_buffer(lbft_sim* sim, uint32_t which, void** device_ptr, size_t* bytes);
 
 void lbft_destroy(lbft_sim* sim);

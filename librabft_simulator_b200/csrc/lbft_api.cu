@@ -82,6 +82,10 @@ struct lbft_sim {
   uint32_t* d_status = nullptr;
   uint32_t* d_rounds = nullptr;
   uint32_t* d_error = nullptr;
+  // d_last_state, d_commit_counts and d_rounds are carved out of ONE allocation, in this order, so that the per-instance
+  // summaries a multi-GPU caller all-gathers travel in a single collective (lbft_device_buffer(5))
+  unsigned char* d_summary = nullptr;
+  size_t summary_bytes = 0;
   lbft_commit* d_logs = nullptr;  // lbft_commit_logs: [I][logs_cap], allocated on first use
   size_t logs_cap = 0;
   uint64_t device_bytes = 0;
@@ -113,8 +117,8 @@ static void free_all(lbft_sim* s) {
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);  // an lbft_run_async may still be in flight
   cudaFree(s->d_seeds); cudaFree(s->d_zx); cudaFree(s->d_zf); cudaFree(s->d_leader); cudaFree(s->d_duration);
-  cudaFree(s->d_period); cudaFree(s->d_weights); cudaFree(s->d_delay_thr); cudaFree(s->d_state); cudaFree(s->d_commit_counts);
-  cudaFree(s->d_lc_round); cudaFree(s->d_last_state); cudaFree(s->d_counters); cudaFree(s->d_status); cudaFree(s->d_rounds);
+  cudaFree(s->d_period); cudaFree(s->d_weights); cudaFree(s->d_delay_thr); cudaFree(s->d_state); cudaFree(s->d_summary);
+  cudaFree(s->d_lc_round); cudaFree(s->d_counters); cudaFree(s->d_status);
   cudaFree(s->d_error); cudaFree(s->d_logs);
   for (int b = 0; b < 2; b++) {
     cudaFreeHost(s->h_seeds[b]);
@@ -259,12 +263,14 @@ int lbft_create(const lbft_config* config, lbft_sim** out_sim) {
   CREATE_TRY(dev_alloc(s, &s->d_weights, N));
   if (!s->hs.delay_thr.empty()) CREATE_TRY(dev_alloc(s, &s->d_delay_thr, s->hs.delay_thr.size()));
   CREATE_TRY(dev_alloc(s, &s->d_state, tiles * L.total_words * s->stride));
-  CREATE_TRY(dev_alloc(s, &s->d_commit_counts, I * N));
+  s->summary_bytes = I * N * sizeof(uint64_t) + I * N * sizeof(uint32_t) + I * sizeof(uint32_t);
+  CREATE_TRY(dev_alloc(s, &s->d_summary, s->summary_bytes));
+  s->d_last_state = reinterpret_cast<uint64_t*>(s->d_summary);
+  s->d_commit_counts = reinterpret_cast<uint32_t*>(s->d_summary + I * N * sizeof(uint64_t));
+  s->d_rounds = s->d_commit_counts + I * N;
   CREATE_TRY(dev_alloc(s, &s->d_lc_round, I * N));
-  CREATE_TRY(dev_alloc(s, &s->d_last_state, I * N));
   CREATE_TRY(dev_alloc(s, &s->d_counters, I * 12));
   CREATE_TRY(dev_alloc(s, &s->d_status, I));
-  CREATE_TRY(dev_alloc(s, &s->d_rounds, I));
   CREATE_TRY(dev_alloc(s, &s->d_error, 1));
   for (int b = 0; b < 2; b++) {
     HostResults& r = s->res[b];
@@ -329,6 +335,7 @@ int lbft_device_buffer(lbft_sim* s, uint32_t which, void** device_ptr, size_t* b
     case 2: *device_ptr = s->d_counters; *bytes = I * 12 * sizeof(uint32_t); break;
     case 3: *device_ptr = s->d_status; *bytes = I * sizeof(uint32_t); break;
     case 4: *device_ptr = s->d_rounds; *bytes = I * sizeof(uint32_t); break;
+    case 5: *device_ptr = s->d_summary; *bytes = s->summary_bytes; break;
     default: return set_error(LBFT_ERR_INVALID, "unknown buffer id");
   }
   return LBFT_OK;

@@ -35,28 +35,37 @@ class _DeviceView:
 
 
 class ShardedResult:
-    """Whole-job summaries after the all-gather, plus this rank's own ``BatchResult`` (``.local``)."""
+    """Whole-job summaries after the all-gather, plus this rank's own ``BatchResult`` (``.local``).  ``block`` is the gathered
+    ``[world, bytes]`` tensor (device memory with NCCL): per rank the last states [I][N] u64, commit counts [I][N] u32 and
+    active rounds [I] u32 of its shard; it is decoded on the host on first access."""
 
-    def __init__(self, local, commit_counts, last_committed_states, active_rounds, lo, hi):
-        self.local, self.lo, self.hi = local, lo, hi
-        self._cc, self._ls, self._ar = commit_counts, last_committed_states, active_rounds
+    def __init__(self, local, block, instances_per_rank, num_nodes, lo, hi):
+        self.local, self.block, self.lo, self.hi = local, block, lo, hi
+        self._shape, self._decoded = (instances_per_rank, num_nodes), None
 
-    @staticmethod
-    def _host(t, dtype):
-        return t.detach().cpu().numpy().view(dtype) if hasattr(t, "detach") else np.asarray(t).view(dtype)
+    def _decode(self):
+        if self._decoded is None:
+            I, N = self._shape
+            b = self.block.detach().cpu().numpy() if hasattr(self.block, "detach") else np.asarray(self.block)
+            b = np.ascontiguousarray(b).reshape(-1, I * N * 12 + I * 4)
+            ns, nc = I * N * 8, I * N * 4
+            self._decoded = (np.ascontiguousarray(b[:, ns:ns + nc]).view(np.uint32).reshape(-1, N),
+                             np.ascontiguousarray(b[:, :ns]).view(np.uint64).reshape(-1, N),
+                             np.ascontiguousarray(b[:, ns + nc:]).view(np.uint32).reshape(-1))
+        return self._decoded
 
     @property
     def commit_counts(self):
         """[all instances, node] ``committed_history().len()``"""
-        return self._host(self._cc, np.uint32)
+        return self._decode()[0]
 
     @property
     def last_committed_states(self):
-        return self._host(self._ls, np.uint64)
+        return self._decode()[1]
 
     @property
     def active_rounds(self):
-        return self._host(self._ar, np.uint32)
+        return self._decode()[2]
 
 
 class ShardedBatchSimulator:
@@ -97,39 +106,38 @@ class ShardedBatchSimulator:
         self.local.set_seeds(seeds[self.lo:self.hi])
 
     # -- the one collective of the path ---------------------------------------------------------------
-    def _device_views(self):
-        """Torch views of the library's device result buffers (NCCL gathers them in place)."""
+    def _device_summary(self):
+        """Torch view of the library's device-resident summary block of this shard: last states [I][N] u64, commit counts
+        [I][N] u32, active rounds [I] u32, contiguous (``lbft_device_buffer(5)``) — NCCL gathers it in place."""
         import torch
         if self._views is None:
-            I, N = self.hi - self.lo, self.num_nodes
-            dev = "cuda:%d" % self.device
-            cc, _ = self.local.device_buffer(0)
-            ls, _ = self.local.device_buffer(1)
-            ar, _ = self.local.device_buffer(4)
-            self._views = (torch.as_tensor(_DeviceView(cc, (I, N), "<i4"), device=dev),
-                           torch.as_tensor(_DeviceView(ls, (I, N), "<i8"), device=dev),
-                           torch.as_tensor(_DeviceView(ar, (I,), "<i4"), device=dev))
+            ptr, nbytes = self.local.device_buffer(5)
+            self._views = torch.as_tensor(_DeviceView(ptr, (nbytes,), "|u1"), device="cuda:%d" % self.device)
         return self._views
 
     def gather(self, local_result=None):
-        """All-gather ``{commit_count[N], state_key[N], rounds}`` of every rank's shard.  On a CUDA backend the
-        sources are the device-resident result buffers; otherwise the host arrays of ``local_result``."""
+        """ONE all-gather of ``{state_key[N], commit_count[N], rounds}`` of every rank's shard, complete when it
+        returns.  On a CUDA backend the source is the device-resident summary block; otherwise the host arrays of
+        ``local_result`` packed the same way.  Returns the gathered ``[world, bytes]`` block (see ``ShardedResult``)."""
         import torch
+        I, N = self.hi - self.lo, self.num_nodes
         on_device = self.dist is not None and self.world > 1 and self.dist.get_backend() == "nccl"
         if on_device:
-            cc, ls, ar = self._device_views()
+            block = self._device_summary()
         else:
-            cc = torch.as_tensor(np.ascontiguousarray(local_result.commit_counts).view(np.int32))
-            ls = torch.as_tensor(np.ascontiguousarray(local_result.last_committed_states).view(np.int64))
-            ar = torch.as_tensor(np.ascontiguousarray(local_result.active_rounds).view(np.int32))
-        d = self.dist if self.world > 1 else None
-        return all_gather_rows(cc, self.world, d), all_gather_rows(ls, self.world, d), all_gather_rows(ar, self.world, d)
+            block = torch.as_tensor(np.concatenate([
+                np.ascontiguousarray(local_result.last_committed_states, dtype=np.uint64).reshape(-1).view(np.uint8),
+                np.ascontiguousarray(local_result.commit_counts, dtype=np.uint32).reshape(-1).view(np.uint8),
+                np.ascontiguousarray(local_result.active_rounds, dtype=np.uint32).reshape(-1).view(np.uint8)]))
+        allb = all_gather_rows(block.reshape(1, -1), self.world, self.dist if self.world > 1 else None)
+        if on_device:
+            torch.cuda.current_stream(allb.device).synchronize()  # the results are complete (and the sources free) on return
+        return allb
 
     def run(self, strict=True):
         """``lbft_run`` on this rank's shard (host seeds in, host summaries out) + the all-gather."""
         res = self.local.run(strict=strict)
-        cc, ls, ar = self.gather(res)
-        return ShardedResult(res, cc, ls, ar, self.lo, self.hi)
+        return ShardedResult(res, self.gather(res), self.hi - self.lo, self.num_nodes, self.lo, self.hi)
 
     def loop_until(self, max_clock, strict=True):
         """``Simulator::new`` + ``loop_until(max_clock)`` for the whole job (simulator.rs:200-250, 380-475)."""
