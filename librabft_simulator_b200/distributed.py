@@ -120,7 +120,6 @@ class ShardedBatchSimulator:
         returns.  On a CUDA backend the source is the device-resident summary block; otherwise the host arrays of
         ``local_result`` packed the same way.  Returns the gathered ``[world, bytes]`` block (see ``ShardedResult``)."""
         import torch
-        I, N = self.hi - self.lo, self.num_nodes
         on_device = self.dist is not None and self.world > 1 and self.dist.get_backend() == "nccl"
         if on_device:
             block = self._device_summary()
