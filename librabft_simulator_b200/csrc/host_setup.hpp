@@ -162,6 +162,13 @@ struct HostSetup {
       if (!strcmp(f, "thread")) use_wide = false;
     }
     tile_stride = use_wide ? 1u : 32u;
+    // LBFT_THREAD_TILE=8|4: sparse warp tiles of the thread kernel (kernels.cuh TILE) — honoured below once the queue mode is
+    // known (plain calendar-queue kernels only)
+    uint32_t want_tile = 32;
+    if (const char* f = std::getenv("LBFT_THREAD_TILE")) {
+      const int v = atoi(f);
+      if (v == 8 || v == 16) want_tile = (uint32_t)v;
+    }
     // lanes per instance: enough for the committee's fan-out, few enough that a warp carries several instances
     // (measured, profiles/README.md r2e: 8 lanes per instance — four instances per warp — win once the batch fills the machine
     // with warps, committees of 64 included: 8 192 x 64 takes 1.14 s against 1.63 s with a warp per instance; below ~4 K
@@ -227,6 +234,8 @@ struct HostSetup {
       if (qscan == 2 && qcap > (use_wide ? 1024u : 64u)) qscan = N <= 5 ? 1u : (c.max_clock <= 4095 ? 3u : 0u);
     }
     p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0, epochs, tds);
+    if (!use_wide && want_tile != 32 && ((qscan == 3 && (want_tile == 8 || N <= 16)) || (qscan == 2 && want_tile == 8)) && !modes && !tds && epochs == 1)
+      tile_stride = want_tile;
     // wide kernel: the whole instance lives in shared memory when four 128-thread blocks (128 / group instances each) of it
     // fit on an SM
     {

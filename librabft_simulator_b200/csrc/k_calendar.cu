@@ -3,6 +3,12 @@
 namespace lbft {
 cudaError_t launch_calendar(const KernelSel& k, const Params& P, cudaStream_t stream) {
   if (k.wide || k.fixed || k.qmode != 3) return cudaErrorInvalidValue;
+  if (k.tile != 32) {  // sparse tiles (plain kernels; the host only asks for them there)
+    if (k.rec || k.res || k.epochs || k.tds) return cudaErrorInvalidValue;
+    if (k.tile == 8) return k.nmax == 16 ? launch_sparse_tiles<16, 3, 8>(P, stream) : (k.nmax == 32 ? launch_sparse_tiles<32, 3, 8>(P, stream) : launch_sparse_tiles<64, 3, 8>(P, stream));
+    if (k.tile == 16) return k.nmax == 16 ? launch_sparse_tiles<16, 3, 16>(P, stream) : cudaErrorInvalidValue;
+    return cudaErrorInvalidValue;
+  }
   if (k.nmax == 16) return launch_thread_variants<16, 3>(k, P, stream);
   if (k.nmax == 32) return launch_thread_variants<32, 3>(k, P, stream);
   return launch_thread_variants<64, 3>(k, P, stream);

@@ -29,8 +29,14 @@ struct LaunchShape {
   static constexpr int kBlocksPerSm = QMODE == 2 ? LBFT_Q2_BLOCKS : 14;
 };
 
-template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, bool EP = false, bool TDS = false>
+// TILE: instances per warp tile.  32 fills every lane; 8 / 4 ("sparse" tiles: the other lanes of the warp retire at once) trade
+// lanes for warps when the batch is too small to fill the GPU with full warps — the instances of a warp serialise through
+// each other's code paths, so a warp of 8 instances finishes far sooner than a warp of 32, and four times as many warps hide
+// each other's latency.  Plain kernels over the calendar queue and the shared-memory queue (whose columns keep their
+// 32-entry pitch); the state layout interleaves TILE instances.
+template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, bool EP = false, bool TDS = false, int TILE = 32>
 __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
+  static_assert(TILE == 32 || ((QMODE == 3 || QMODE == 2) && !REC && !RES && !EP && !TDS), "sparse tiles: plain kernels over the calendar / shared-memory queue");
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
   // scattered 8-byte reads of a warp in ~1-2 wavefronts; reading them through L1 from global memory instead was
   // measured 1.5x slower for the whole kernel (44.1 vs 28.9 ms).
@@ -46,10 +52,11 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
   if (thr_fits)
     for (uint32_t i = threadIdx.x; i < P.delay_kmax + 2; i += blockDim.x) s_thr[i] = P.delay_thr[i];
   __syncthreads();
-  const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
-  if (inst >= P.num_instances) return;
-  const uint32_t tile = inst >> 5, lane = inst & 31;
-  TileMem<32> mem{P.state + (size_t)tile * P.L.total_words * 32, lane};
+  const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t tile = gthread >> 5, lane = gthread & 31;
+  const uint32_t inst = tile * TILE + lane;
+  if (lane >= TILE || inst >= P.num_instances) return;
+  TileMem<TILE> mem{P.state + (size_t)tile * P.L.total_words * TILE, lane};
   uint32_t* sk = nullptr;
   uint16_t* sd = nullptr;
   if (QMODE == 2) {
@@ -58,7 +65,7 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<32>, NMAX, QMODE, FIXED, REC, RES, 1, EP, TDS> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  Core<TileMem<TILE>, NMAX, QMODE, FIXED, REC, RES, 1, EP, TDS> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
   if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
   else core.init(P.seeds[inst]);
   core.run();
@@ -124,6 +131,7 @@ struct KernelSel {
   int group;   // wide kernel: lanes per instance (8 / 32)
   bool epochs; // Layout::epochs > 1: the instantiation with the epoch machinery (plain kernels only)
   bool tds;    // LBFT_FLAG_TRUE_DATA_SYNC (plain single-epoch thread kernels only)
+  int tile;    // thread kernel: instances per warp tile (32; 8 / 4 = sparse tiles, plain calendar-queue kernels)
   int nmax;    // 16 / 32 / 64: width of the author masks
   int qmode;   // Layout::queue_scan
   bool fixed, rec, res;
@@ -137,6 +145,14 @@ cudaError_t launch_heap(const KernelSel& k, const Params& P, cudaStream_t stream
 cudaError_t launch_wide(const KernelSel& k, const Params& P, cudaStream_t stream);
 
 // Shared by the launchers of the thread-per-instance kernel.
+template <int NMAX, int QM, int TILE>
+inline cudaError_t launch_sparse_tiles(const Params& P, cudaStream_t stream) {
+  constexpr int T = LaunchShape<QM>::kThreads;
+  const uint32_t tiles = (P.num_instances + TILE - 1) / TILE, blocks = (tiles * 32 + T - 1) / T;
+  const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2) : 0;
+  lbft_event_loop_kernel<NMAX, QM, false, false, false, false, false, TILE><<<blocks, T, dyn, stream>>>(P);
+  return cudaGetLastError();
+}
 template <int NMAX, int QM>
 inline cudaError_t launch_thread_variants(const KernelSel& k, const Params& P, cudaStream_t stream) {
   constexpr int T = LaunchShape<QM>::kThreads;

@@ -426,6 +426,7 @@ static KernelSel select_kernel(const lbft_sim* s) {
   k.group = (int)s->hs.wide_group;
   k.epochs = s->P.L.epochs > 1;
   k.tds = s->P.L.tds != 0;
+  k.tile = (int)s->stride;
   k.qmode = (int)s->P.L.queue_scan;
   k.nmax = (k.qmode == 1 || k.qmode == 2) ? 16 : (s->N <= 16 ? 16 : (s->N <= 32 ? 32 : 64));
   k.rec = s->P.record_rs != 0;
@@ -444,8 +445,8 @@ static std::string kernel_name(const lbft_sim* s) {
   if (k.wide)
     snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d,%s,%d,%s>", k.nmax, k.qmode, k.smem ? "true" : "false", k.group, k.epochs ? "true" : "false");
   else
-    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s,%s,%s>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
-             k.res ? "true" : "false", k.epochs ? "true" : "false", k.tds ? "true" : "false");
+    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s,%s,%s,%d>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
+             k.res ? "true" : "false", k.epochs ? "true" : "false", k.tds ? "true" : "false", k.tile);
   return buf;
 }
 

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_gpu_true_data_sync_matches_the_oracle_variant(oracle, nodes, count, max_clock, kw):
     seeds = np.arange(900, 900 + count, dtype=np.uint64)
     sim, g = gpu_run(seeds, nodes, max_clock, true_data_sync=True, **dict(kw))
-    assert sim.kernel_info().endswith(",true>") and sim.kernel_info().startswith("lbft_event_loop_kernel")
+    assert sim.kernel_info().endswith(",true,32>") and sim.kernel_info().startswith("lbft_event_loop_kernel")   # <.., TDS, TILE>
     assert ((g.status & ~np.uint32(64)) == 1).all(), np.unique(g.status)
     assert_same(oracle.run(seeds, nodes, max_clock, flags=4, **kw), g, "true data-sync N=%d" % nodes)
     for inst in (0, count - 1):

@@ -24,7 +24,7 @@ def test_automatic_choice(monkeypatch):
         picks[name] = sim.kernel_info()
         sim.close()
     assert picks["config2"] == "lbft_wide_kernel<16,2,true,32,false>"      # a warp per instance, whole instance in shared memory
-    assert picks["config3"] == picks["mid4"] == "lbft_event_loop_kernel<16,2,true,false,false,false>"
+    assert picks["config3"] == picks["mid4"] == "lbft_event_loop_kernel<16,2,true,false,false,false,false,32>"
     assert picks["config5"] == "lbft_wide_kernel<16,2,false,8,false>"      # 8 lanes per instance, four instances per warp
     assert picks["small64"] == "lbft_wide_kernel<64,3,false,32,false>"     # (8 192 x 64 selects <64,3,false,8,false>)
     assert picks["long7"] == "lbft_wide_kernel<16,0,false,32,false>"       # beyond the 14-bit times of the compact queue
