@@ -101,6 +101,8 @@ def build_oracle_native():
 
 
 def build_hostcore(force=False):
+    if os.environ.get("LBFT_HOSTCORE_PATH"):  # an alternatively built copy (A/B of compile-time switches)
+        return os.environ["LBFT_HOSTCORE_PATH"]
     srcs = [os.path.join(HOSTCORE_DIR, "hostcore.cpp")] + [
         os.path.join(CSRC, f) for f in ("sim_core.cuh", "sim_params.h", "host_setup.hpp")]
     if not force and _newer(HOSTCORE_PATH, srcs):

@@ -161,14 +161,25 @@ struct HostSetup {
       if (!strcmp(f, "wide") && !modes && !tds) use_wide = true;
       if (!strcmp(f, "thread")) use_wide = false;
     }
-    tile_stride = use_wide ? 1u : 32u;
-    // LBFT_THREAD_TILE=8|4: sparse warp tiles of the thread kernel (kernels.cuh TILE) — honoured below once the queue mode is
-    // known (plain calendar-queue kernels only)
+    // Sparse warp tiles of the thread kernel (kernels.cuh TILE: 8 or 16 instances per warp, the other lanes retire at once):
+    // the instances of a warp serialise through each other's code paths, so as long as the batch does not fill the machine
+    // with full warps (2 048 warps of <= 128 registers = one wave on 148 SMs), fewer instances per warp finish sooner.
+    // Measured on BASELINE configs[4] (16 384 x 7, profiles/r2j_ab_tiles.txt, r2k): 8 per warp 59.3 ms, 16 per warp 72.8, full
+    // tiles 88.9, the wide kernel (8 lanes per instance) 76.2.  So for committees of 6..16 (calendar queue, plain
+    // single-epoch handles): about one wave of 8-instance warps -> tile 8, of 16-instance warps -> tile 16, more -> full
+    // tiles; below that the wide kernel.  LBFT_THREAD_TILE=8|16 / LBFT_FORCE_KERNEL override (A/B runs); honoured further
+    // down, once the queue mode is known.
     uint32_t want_tile = 32;
+    const bool env_family = std::getenv("LBFT_FORCE_KERNEL") != nullptr;
     if (const char* f = std::getenv("LBFT_THREAD_TILE")) {
       const int v = atoi(f);
       if (v == 8 || v == 16) want_tile = (uint32_t)v;
+    } else if (!env_family && use_wide && N >= 6 && N <= 16 && c.max_clock <= 4095 && c.num_instances > 12288 &&
+               c.commands_per_epoch >= rcap && c.queue_cap <= 0xfff0u) {
+      use_wide = false;
+      want_tile = c.num_instances <= 24576 ? 8u : (c.num_instances <= 49152 ? 16u : 32u);
     }
+    tile_stride = use_wide ? 1u : 32u;
     // lanes per instance: enough for the committee's fan-out, few enough that a warp carries several instances
     // (measured, profiles/README.md r2e: 8 lanes per instance — four instances per warp — win once the batch fills the machine
     // with warps, committees of 64 included: 8 192 x 64 takes 1.14 s against 1.63 s with a warp per instance; below ~4 K

@@ -2,7 +2,7 @@
 #include "kernels.cuh"
 namespace lbft {
 cudaError_t launch_wide(const KernelSel& k, const Params& P, cudaStream_t stream) {
-  if (!k.wide || k.fixed || k.rec || k.res) return cudaErrorInvalidValue;
+  if (!k.wide || (k.fixed != FX_NONE && k.fixed != FX_COMMITTEE64) || k.rec || k.res) return cudaErrorInvalidValue;
   switch (k.qmode) {
     case 2: return k.smem ? launch_wide_groups<16, 2, true>(k, P, stream) : launch_wide_groups<16, 2, false>(k, P, stream);
     case 1: return launch_wide_groups<16, 1, false>(k, P, stream);

@@ -34,7 +34,7 @@ struct LaunchShape {
 // each other's code paths, so a warp of 8 instances finishes far sooner than a warp of 32, and four times as many warps hide
 // each other's latency.  Plain kernels over the calendar queue and the shared-memory queue (whose columns keep their
 // 32-entry pitch); the state layout interleaves TILE instances.
-template <int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, bool EP = false, bool TDS = false, int TILE = 32>
+template <int NMAX, int QMODE, int FX = FX_NONE, bool REC = false, bool RES = false, bool EP = false, bool TDS = false, int TILE = 32>
 __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMODE>::kBlocksPerSm) lbft_event_loop_kernel(const __grid_constant__ Params P) {
   static_assert(TILE == 32 || ((QMODE == 3 || QMODE == 2) && !REC && !RES && !EP && !TDS), "sparse tiles: plain kernels over the calendar / shared-memory queue");
   // The ziggurat layers are indexed by a random byte per lane: a per-block shared-memory copy (4 KB) serves the 32
@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
   const uint32_t tile = gthread >> 5, lane = gthread & 31;
   const uint32_t inst = tile * TILE + lane;
   if (lane >= TILE || inst >= P.num_instances) return;
-  TileMem<TILE> mem{P.state + (size_t)tile * P.L.total_words * TILE, lane};
+  const uint32_t total_words = FX ? fixed_layout(FX).total_words : P.L.total_words;
+  TileMem<TILE> mem{P.state + (size_t)tile * total_words * TILE, lane};
   uint32_t* sk = nullptr;
   uint16_t* sd = nullptr;
   if (QMODE == 2) {
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<TILE>, NMAX, QMODE, FIXED, REC, RES, 1, EP, TDS> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  Core<TileMem<TILE>, NMAX, QMODE, FX, REC, RES, 1, EP, TDS> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
   if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
   else core.init(P.seeds[inst]);
   core.run();
@@ -95,21 +96,22 @@ LBFT_LAYOUT_FN uint32_t wide_smem_words_per_group(const Layout& L, int qmode, bo
 
 // SMEM: the instance's state words live in shared memory for the whole run; only the chain table (and the epoch table) is
 // copied to the instance's global extent at the end, for lbft_commit_log / lbft_commit_logs.
-template <int NMAX, int QMODE, bool SMEM, int G, bool EP = false>
+template <int NMAX, int QMODE, bool SMEM, int G, bool EP = false, int FX = FX_NONE>
 __global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(8) uint32_t s_wide[];
   constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
   const uint32_t grp = threadIdx.x / G, wl = threadIdx.x % G;
   const uint32_t inst = blockIdx.x * kPerBlock + grp;
   if (inst >= P.num_instances) return;  // whole groups leave together: everything below is group-uniform
-  uint32_t* base = s_wide + (size_t)grp * wide_smem_words_per_group(P.L, QMODE, SMEM);
+  const Layout KL = FX ? fixed_layout(FX) : P.L;
+  uint32_t* base = s_wide + (size_t)grp * wide_smem_words_per_group(KL, QMODE, SMEM);
   WideScratch* ws = reinterpret_cast<WideScratch*>(base);
   uint32_t* sk = base + wide_scratch_words();
-  uint16_t* sd = reinterpret_cast<uint16_t*>(sk + P.L.queue_cap);
-  uint32_t* gstate = P.state + (size_t)inst * P.L.total_words;
-  uint32_t* state = SMEM ? sk + wide_queue_words(P.L.queue_cap, QMODE) : gstate;
+  uint16_t* sd = reinterpret_cast<uint16_t*>(sk + KL.queue_cap);
+  uint32_t* gstate = P.state + (size_t)inst * KL.total_words;
+  uint32_t* state = SMEM ? sk + wide_queue_words(KL.queue_cap, QMODE) : gstate;
   TileMem<1> mem{state, 0};
-  Core<TileMem<1>, NMAX, QMODE, false, false, false, G, EP> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
+  Core<TileMem<1>, NMAX, QMODE, FX, false, false, G, EP> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
   core.wl = wl;
   core.gm = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(G - 1)));
   core.ws = ws;
@@ -134,7 +136,8 @@ struct KernelSel {
   int tile;    // thread kernel: instances per warp tile (32; 8 / 4 = sparse tiles, plain calendar-queue kernels)
   int nmax;    // 16 / 32 / 64: width of the author masks
   int qmode;   // Layout::queue_scan
-  bool fixed, rec, res;
+  int fixed;   // FX_* (sim_params.h): the instantiation with that compile-time layout; FX_NONE = generic
+  bool rec, res;
 };
 
 // One per translation unit; each returns cudaErrorInvalidValue if the selection is not one of its instantiations.
@@ -145,12 +148,12 @@ cudaError_t launch_heap(const KernelSel& k, const Params& P, cudaStream_t stream
 cudaError_t launch_wide(const KernelSel& k, const Params& P, cudaStream_t stream);
 
 // Shared by the launchers of the thread-per-instance kernel.
-template <int NMAX, int QM, int TILE>
+template <int NMAX, int QM, int TILE, int FX = FX_NONE>
 inline cudaError_t launch_sparse_tiles(const Params& P, cudaStream_t stream) {
   constexpr int T = LaunchShape<QM>::kThreads;
   const uint32_t tiles = (P.num_instances + TILE - 1) / TILE, blocks = (tiles * 32 + T - 1) / T;
   const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2) : 0;
-  lbft_event_loop_kernel<NMAX, QM, false, false, false, false, false, TILE><<<blocks, T, dyn, stream>>>(P);
+  lbft_event_loop_kernel<NMAX, QM, FX, false, false, false, false, TILE><<<blocks, T, dyn, stream>>>(P);
   return cudaGetLastError();
 }
 template <int NMAX, int QM>
@@ -160,29 +163,29 @@ inline cudaError_t launch_thread_variants(const KernelSel& k, const Params& P, c
   const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2) : 0;
   if (k.tds) {
     if (k.rec || k.res || k.epochs) return cudaErrorInvalidValue;  // (refused at lbft_create)
-    lbft_event_loop_kernel<NMAX, QM, false, false, false, false, true><<<blocks, T, dyn, stream>>>(P);
+    lbft_event_loop_kernel<NMAX, QM, FX_NONE, false, false, false, true><<<blocks, T, dyn, stream>>>(P);
   } else if (k.epochs) {
     if (k.rec || k.res) return cudaErrorInvalidValue;  // (refused at lbft_create)
-    lbft_event_loop_kernel<NMAX, QM, false, false, false, true><<<blocks, T, dyn, stream>>>(P);
-  } else if (k.rec && k.res) lbft_event_loop_kernel<NMAX, QM, false, true, true><<<blocks, T, dyn, stream>>>(P);
-  else if (k.res) lbft_event_loop_kernel<NMAX, QM, false, false, true><<<blocks, T, dyn, stream>>>(P);
-  else if (k.rec) lbft_event_loop_kernel<NMAX, QM, false, true><<<blocks, T, dyn, stream>>>(P);
+    lbft_event_loop_kernel<NMAX, QM, FX_NONE, false, false, true><<<blocks, T, dyn, stream>>>(P);
+  } else if (k.rec && k.res) lbft_event_loop_kernel<NMAX, QM, FX_NONE, true, true><<<blocks, T, dyn, stream>>>(P);
+  else if (k.res) lbft_event_loop_kernel<NMAX, QM, FX_NONE, false, true><<<blocks, T, dyn, stream>>>(P);
+  else if (k.rec) lbft_event_loop_kernel<NMAX, QM, FX_NONE, true><<<blocks, T, dyn, stream>>>(P);
   else lbft_event_loop_kernel<NMAX, QM><<<blocks, T, dyn, stream>>>(P);
   return cudaGetLastError();
 }
 
-template <int NMAX, int QM, bool SMEM, int G, bool EP>
+template <int NMAX, int QM, bool SMEM, int G, bool EP, int FX = FX_NONE>
 inline cudaError_t launch_wide_variant(const Params& P, cudaStream_t stream) {
   constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
   const uint32_t blocks = (P.num_instances + kPerBlock - 1) / kPerBlock;
   const size_t dyn = (size_t)kPerBlock * wide_smem_words_per_group(P.L, QM, SMEM) * sizeof(uint32_t);
   static size_t attr_set = 48 * 1024;  // (per instantiation; two threads racing set the same or a larger value)
   if (dyn > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lbft_wide_kernel<NMAX, QM, SMEM, G, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaError_t e = cudaFuncSetAttribute(lbft_wide_kernel<NMAX, QM, SMEM, G, EP, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     attr_set = dyn;
   }
-  lbft_wide_kernel<NMAX, QM, SMEM, G, EP><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
+  lbft_wide_kernel<NMAX, QM, SMEM, G, EP, FX><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
   return cudaGetLastError();
 }
 // the lanes-per-instance / epoch dimensions of an instantiation family (the host only selects these combinations)
@@ -191,6 +194,10 @@ inline cudaError_t launch_wide_groups(const KernelSel& k, const Params& P, cudaS
   if (k.epochs) {
     if (SMEM || k.group != 32) return cudaErrorInvalidValue;
     return launch_wide_variant<NMAX, QM, false, 32, true>(P, stream);
+  }
+  if (k.fixed == FX_COMMITTEE64) {  // (lbft_api.cu select_kernel: 64 authors, calendar queue, 8 lanes per instance, state in HBM)
+    if (NMAX != 64 || QM != 3 || SMEM || k.group != 8) return cudaErrorInvalidValue;
+    return launch_wide_variant<64, 3, false, 8, false, (NMAX == 64 && QM == 3 && !SMEM) ? FX_COMMITTEE64 : FX_NONE>(P, stream);
   }
   if (k.group == 8) return launch_wide_variant<NMAX, QM, SMEM, 8, false>(P, stream);
   return launch_wide_variant<NMAX, QM, SMEM, 32, false>(P, stream);

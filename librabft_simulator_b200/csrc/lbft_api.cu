@@ -431,11 +431,19 @@ static KernelSel select_kernel(const lbft_sim* s) {
   k.nmax = (k.qmode == 1 || k.qmode == 2) ? 16 : (s->N <= 16 ? 16 : (s->N <= 32 ? 32 : 64));
   k.rec = s->P.record_rs != 0;
   k.res = s->P.resumable != 0;
-  // the default four-author layout has a kernel instantiation with compile-time field offsets
-  constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
-  const bool plain_model = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0 &&
-                           s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
-  k.fixed = !k.wide && k.qmode == 2 && plain_model && !k.rec && !k.res && !s->P.L.tds && memcmp(&s->P.L, &kFixed, sizeof(Layout)) == 0;
+  // shapes with a kernel instantiation with compile-time field offsets (sim_params.h fixed_layout): the handle's layout must
+  // be bit-identical and the delay model the reference's (LogNormal served by the threshold table)
+  constexpr Layout kDefault4 = fixed_layout(FX_DEFAULT4), kPart7 = fixed_layout(FX_PART7), kCommittee64 = fixed_layout(FX_COMMITTEE64);
+  const bool table_delay = s->P.delay_kind == LBFT_DELAY_LOGNORMAL && !s->P.delay_const && s->P.delay_kmax != 0;
+  const bool plain_model = table_delay && s->P.delay_kmax + 2 <= kThrSmem && s->P.silent_mask == 0;
+  const bool plain_handle = !k.rec && !k.res && !k.tds && !k.epochs;
+  k.fixed = FX_NONE;
+  if (!k.wide && k.qmode == 2 && plain_model && plain_handle && memcmp(&s->P.L, &kDefault4, sizeof(Layout)) == 0) k.fixed = FX_DEFAULT4;
+  else if (!k.wide && k.qmode == 3 && k.tile == 8 && plain_model && plain_handle && memcmp(&s->P.L, &kPart7, sizeof(Layout)) == 0) k.fixed = FX_PART7;
+  else if (k.wide && k.qmode == 3 && k.group == 8 && !k.smem && table_delay && plain_handle && memcmp(&s->P.L, &kCommittee64, sizeof(Layout)) == 0)
+    k.fixed = FX_COMMITTEE64;
+  if (const char* f = std::getenv("LBFT_NO_FIXED_SHAPES"))  // A/B runs: the generic instantiations for the shapes other than the default one
+    if (atoi(f) != 0 && k.fixed != FX_DEFAULT4) k.fixed = FX_NONE;
   return k;
 }
 // ... spelled like the symbol ncu / cuobjdump show.
@@ -443,9 +451,9 @@ static std::string kernel_name(const lbft_sim* s) {
   const KernelSel k = select_kernel(s);
   char buf[96];
   if (k.wide)
-    snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d,%s,%d,%s>", k.nmax, k.qmode, k.smem ? "true" : "false", k.group, k.epochs ? "true" : "false");
+    snprintf(buf, sizeof buf, "lbft_wide_kernel<%d,%d,%s,%d,%s,%d>", k.nmax, k.qmode, k.smem ? "true" : "false", k.group, k.epochs ? "true" : "false", k.fixed);
   else
-    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%s,%s,%s,%s,%s,%d>", k.nmax, k.qmode, k.fixed ? "true" : "false", k.rec ? "true" : "false",
+    snprintf(buf, sizeof buf, "lbft_event_loop_kernel<%d,%d,%d,%s,%s,%s,%s,%d>", k.nmax, k.qmode, k.fixed, k.rec ? "true" : "false",
              k.res ? "true" : "false", k.epochs ? "true" : "false", k.tds ? "true" : "false", k.tile);
   return buf;
 }
@@ -457,7 +465,7 @@ static int enqueue_kernel(lbft_sim* s) {
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
   const KernelSel k = select_kernel(s);
   cudaError_t e = k.wide ? launch_wide(k, s->P, s->stream)
-                  : k.fixed ? launch_fixed(k, s->P, s->stream)
+                  : k.fixed == FX_DEFAULT4 ? launch_fixed(k, s->P, s->stream)
                   : (k.qmode == 1 || k.qmode == 2) ? launch_scan(k, s->P, s->stream)
                   : k.qmode == 3 ? launch_calendar(k, s->P, s->stream)
                                  : launch_heap(k, s->P, s->stream);

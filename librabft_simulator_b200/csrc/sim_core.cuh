@@ -280,10 +280,11 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 
 // QMODE: 0 binary heap (3-word entries, HBM) | 1 scan queue, 64-bit keys in HBM | 2 scan queue, 32-bit keys +
 // 16-bit payload words in shared memory (small committees, short horizons) | 3 calendar queue in HBM
-// FIXED: the layout is the compile-time constant make_layout(4, 128, 64, 32, 0, 2) (BASELINE configs 1-3: four authors,
-// default capacities) instead of the launch parameter block: every field offset folds into an immediate.  The host
-// only selects it for the reference's own model (LogNormal delay served by the threshold table, no silent nodes, no
-// partitions), so those extension branches are compiled out as well.
+// FX (FIXED = FX != 0): the layout is the compile-time constant fixed_layout(FX) (sim_params.h: the default four-author
+// shape of BASELINE configs 1-3, the seven-author partition shape of configs[4], the 64-author shape of configs[3])
+// instead of the launch parameter block: every field offset folds into an immediate.  The host only selects one for
+// the reference's own delay model (LogNormal served by the threshold table), so the other delay branches — and, where
+// the shape excludes them, silent nodes and partitions — are compiled out as well.
 // REC: keep DataWriter's round-switch table (LBFT_FLAG_ROUND_SWITCHES, Params::record_rs).  A template parameter rather
 // than a run-time test so that the non-recording instantiations carry no trace of it (the run-time test measured
 // +0.8..2.0 % on the generic kernels, profiles/README.md).
@@ -303,14 +304,16 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // and the response's records are inserted by the requester (what data_sync.rs:183-240 is written for), instead of the
 // reference simulator's dispatch to the requester itself (simulator.rs:446).  An opt-in NON-PARITY
 // variant; plain thread-per-instance kernels only.
-template <class Mem, int NMAX, int QMODE, bool FIXED = false, bool REC = false, bool RES = false, int G = 1, bool EP = false,
+template <class Mem, int NMAX, int QMODE, int FX = 0, bool REC = false, bool RES = false, int G = 1, bool EP = false,
           bool TDS = false>
 struct Core {
+  static constexpr bool FIXED = FX != FX_NONE;                               // compile-time layout, reference delay model
+  static constexpr bool MAY_SILENT = FX == FX_NONE || FX == FX_COMMITTEE64;  // silent nodes (extension D.2) reachable
   static_assert(!(FIXED && EP), "the compile-time layout is single-epoch");
   static_assert(!(TDS && (FIXED || REC || RES || EP || G > 1)), "true data-sync: plain single-epoch thread kernels only");
   static_assert(!(FIXED && (REC || RES)), "the compile-time layout has neither a round-switch table nor a save area");
   static_assert(G == 1 || G == 8 || G == 16 || G == 32, "one thread, or a group of 8 / 16 / 32 lanes per instance");
-  static_assert(G == 1 || !(FIXED || REC || RES), "the wide kernel has no fixed-layout / recording / resumable variants");
+  static_assert(G == 1 || !(REC || RES), "the wide kernel has no recording / resumable variants");
   static constexpr bool WIDE = G > 1;
   static constexpr int QS = WIDE ? 1 : 32;  // QMODE 2: stride between queue entries in shared memory (a column per lane / contiguous)
   uint32_t wl = 0;            // this thread's lane inside the group (0 when G == 1)
@@ -345,14 +348,14 @@ struct Core {
   uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify, dedup;
   uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
   uint32_t cal_t, cal_free, cal_next;  // QMODE 3: current bucket time, pool free list head, pool bump pointer
-  int32_t part_clock;  // partition plan: the clock part_open was computed for (-1: never)
-  uint64_t part_open;  // ... and the windows open at that clock
+  int32_t part_until;  // partition plan: part_open holds for every clock below this (0: not computed yet)
+  uint64_t part_open;  // ... the windows open in that span, a bit per window
   uint32_t rs_pend;  // recording only: node << 16 | active round of the round switch not yet stamped with a pop time (0: none)
   uint32_t cc0, cc1, cc2, cc3;  // chain cache: (round << 16) | previous QC round
 
   LBFT_HD Core(const Params& p, Mem mem, const double* zx_, const double* zf_, const double* thr_, uint32_t* sk_ = nullptr,
                uint16_t* sd_ = nullptr)
-      : P(p), L(FIXED ? make_layout(4, 128, 64, 32, 0, 2) : p.L), m(mem), zx(zx_), zf(zf_), thr(thr_), sk(sk_), sd(sd_) {}
+      : P(p), L(FIXED ? fixed_layout(FX) : p.L), m(mem), zx(zx_), zf(zf_), thr(thr_), sk(sk_), sd(sd_) {}
 
   // ------------------------------------------------------------------------------------------
   // RNG (rand_xoshiro 0.6.0 / rand 0.8.3 / rand_distr 0.4.0)
@@ -1265,17 +1268,26 @@ struct Core {
   // ------------------------------------------------------------------------------------------
   // network sends: schedule_network_event (simulator.rs:266-269) + partition drop (extension)
   // ------------------------------------------------------------------------------------------
-  // The windows open at the current clock are found once per clock value (part_clock / part_open: a bit per window),
-  // so a send only looks at the plan while some window is open.
+  // The set of open windows only changes when the clock crosses a window boundary: it is recomputed then (part_until =
+  // the next boundary after the clock), so a send only looks at the plan while some window is open.  Committees of <= 16
+  // with <= 4 windows (BASELINE configs[4]) keep the open windows' author masks themselves in part_open, 16 bits per
+  // window, and a send tests all of them at once without touching memory; otherwise part_open has a bit per open window.
+  LBFT_HD bool packed_plan() const { return NMAX <= 16 && L.part_windows <= 4; }
   LBFT_HD bool partitioned(uint32_t a, uint32_t b2) {  // EXTENSION
-    if (part_clock != clock) {
-      part_clock = clock;
+    if (clock >= part_until) {
       part_open = 0;
+      int32_t until = 0x7fffffff;
       for (uint32_t k = 0; k < L.part_windows; k++) {
-        int32_t t0 = (int32_t)m.ld(L.part_base + 4 * k), t1 = (int32_t)m.ld(L.part_base + 4 * k + 1);
-        if (clock >= t0 && clock < t1) part_open |= 1ULL << k;
+        const int32_t t0 = (int32_t)m.ld(L.part_base + 4 * k), t1 = (int32_t)m.ld(L.part_base + 4 * k + 1);
+        if (clock < t0) { if (t0 < until) until = t0; }
+        else if (clock < t1) {
+          part_open |= packed_plan() ? (uint64_t)(m.ld(L.part_base + 4 * k + 2) & 0xffffu) << (16 * k) : 1ULL << k;
+          if (t1 < until) until = t1;
+        }
       }
+      part_until = until;
     }
+    if (packed_plan()) return (((part_open >> a) ^ (part_open >> b2)) & 0x0001000100010001ULL) != 0;
     for (uint64_t open = part_open; open; open &= open - 1) {
       const uint32_t k = ctz64(open);
       uint64_t mask = m.ld(L.part_base + 4 * k + 2) | ((uint64_t)m.ld(L.part_base + 4 * k + 3) << 32);
@@ -1327,7 +1339,7 @@ struct Core {
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
     cal_t = 0; cal_free = PAY_NONE; cal_next = 0;
-    part_clock = -1; part_open = 0;
+    part_until = 0; part_open = 0;
     if (REC) {
       rs_pend = 0;
       for (uint32_t w = 0; w < N * (L.round_cap + 1); w++) m.st(rs_table_base(L) + w, 0);
@@ -1410,7 +1422,7 @@ struct Core {
       proc2 += kind == EV_RESPONSE;
       proc3 += kind == EV_TIMER;
       // EXTENSION D.2: silent nodes handle nothing and answer no request
-      if (!FIXED && P.silent_mask) {
+      if (MAY_SILENT && P.silent_mask) {
         bool drop = (P.silent_mask >> receiver) & 1;
         if (kind == EV_REQUEST && ((P.silent_mask >> sender) & 1)) drop = true;
         if (drop) {
@@ -1506,7 +1518,7 @@ struct Core {
         // Wide kernel, table-served LogNormal delay: the normal deviates of the fan-out are drawn first (the RNG stream is
         // sequential), then each lane turns its share of them into delays, then the events are queued in list order.
         // Nothing else draws from the stream or takes a creation stamp in between, so the order of both is unchanged.
-        const bool staged = WIDE && list.len > 1 && P.delay_kind == 0u && !P.delay_const && P.delay_kmax != 0;
+        const bool staged = WIDE && list.len > 1 && (FIXED || (P.delay_kind == 0u && !P.delay_const && P.delay_kmax != 0));
         if (staged) {
           for (uint32_t i = 0; i < list.len; i++) ws->z[i] = standard_normal();
           grp_sync();
@@ -1565,7 +1577,7 @@ struct Core {
   LBFT_HD void restore_regs() {
     const uint32_t b = res_area_base(L, REC);
     uint32_t w = b;
-    part_clock = -1; part_open = 0;  // recomputed at the first send
+    part_until = 0; part_open = 0;  // recomputed at the first send
     uint64_t sx[4];
     for (int i = 0; i < 4; i++) { uint64_t lo = m.ld(w++); uint64_t hi = m.ld(w++); sx[i] = lo | (hi << 32); }
     s0 = sx[0]; s1 = sx[1]; s2 = sx[2]; s3 = sx[3];

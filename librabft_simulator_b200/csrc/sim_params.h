@@ -165,6 +165,21 @@ LBFT_LAYOUT_FN Layout make_layout(uint32_t N, uint32_t round_cap, uint32_t queue
   return L;
 }
 
+// Shapes with a kernel instantiation whose layout is a compile-time constant (sim_core.cuh FX): every field offset folds
+// into an immediate and the extension branches the shape cannot reach are compiled out.  The host selects one only when the
+// handle's layout is bit-identical to the constant and the delay model is the reference's (LogNormal served by the
+// threshold table); every other handle runs the generic instantiations.
+//   FX_DEFAULT4     four authors, default capacities, shared-memory queue (BASELINE configs 1-3), thread kernel
+//   FX_PART7        seven authors, four partition windows, max_clock 1000, calendar queue (BASELINE configs[4]), thread
+//                   kernel with 8-instance warp tiles
+//   FX_COMMITTEE64  64 authors, max_clock 1000, calendar queue (BASELINE configs[3]; voting rights and silent nodes stay
+//                   run-time parameters), wide kernel with 8 lanes per instance
+enum : int { FX_NONE = 0, FX_DEFAULT4 = 1, FX_PART7 = 2, FX_COMMITTEE64 = 3 };
+LBFT_LAYOUT_FN Layout fixed_layout(int fx) {
+  return fx == FX_PART7 ? make_layout(7, 128, 512, 64, 4, 3, 1000)
+                        : (fx == FX_COMMITTEE64 ? make_layout(64, 128, 32768, 512, 0, 3, 1000) : make_layout(4, 128, 64, 32, 0, 2));
+}
+
 LBFT_LAYOUT_FN uint32_t rs_table_base(const Layout& L) { return L.pay_base + L.payload_cap * L.pay_words; }
 LBFT_LAYOUT_FN uint32_t res_area_base(const Layout& L, bool record_rs) {
   return rs_table_base(L) + (record_rs ? L.num_nodes * (L.round_cap + 1) : 0);

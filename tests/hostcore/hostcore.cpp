@@ -39,25 +39,31 @@ static void run_all(const Params& P, std::vector<uint32_t>& state, const double*
   else run_all_ep<NMAX, QMODE, REC, RES, false>(P, state, zx, zf);
 }
 
-// The bench kernel's instantiation (compile-time layout, sim_core.cuh FIXED) on the host: selected exactly as lbft_api.cu
-// select_kernel does, so that the default four-author configurations of the CPU tests exercise the very code the bench runs.
-static void run_all_fixed(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
+// The instantiations with a compile-time layout (sim_core.cuh FX, sim_params.h fixed_layout) on the host: selected the way
+// lbft_api.cu select_kernel does (minus the kernel family / tile / lane-group conditions, which do not exist here), so that
+// the CPU tests of those shapes exercise the very state machine the BASELINE configurations run on the GPU.
+template <int NMAX, int QMODE, int FX>
+static void run_all_fx(const Params& P, std::vector<uint32_t>& state, const double* zx, const double* zf) {
   for (uint32_t inst = 0; inst < P.num_instances; inst++) {
     uint32_t tile = inst / 32, lane = inst % 32;
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
-    std::vector<uint32_t> sk((size_t)P.L.queue_cap * 32);
-    std::vector<uint16_t> sd((size_t)P.L.queue_cap * 32);
-    Core<TileMem<32>, 16, 2, true> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
+    std::vector<uint32_t> sk(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);
+    std::vector<uint16_t> sd(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);
+    Core<TileMem<32>, NMAX, QMODE, FX> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
     core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);
   }
 }
-static bool fixed_selected(const Params& P) {
-  constexpr Layout kFixed = make_layout(4, 128, 64, 32, 0, 2);
-  const bool plain_model = P.delay_kind == LBFT_DELAY_LOGNORMAL && !P.delay_const && P.delay_kmax != 0 && P.delay_kmax + 2 <= 256 &&
-                           P.silent_mask == 0;
-  return P.L.queue_scan == 2 && plain_model && !P.record_rs && !P.resumable && memcmp(&P.L, &kFixed, sizeof(Layout)) == 0;
+static int fixed_selected(const Params& P) {
+  constexpr Layout kDefault4 = fixed_layout(FX_DEFAULT4), kPart7 = fixed_layout(FX_PART7), kCommittee64 = fixed_layout(FX_COMMITTEE64);
+  const bool table_delay = P.delay_kind == LBFT_DELAY_LOGNORMAL && !P.delay_const && P.delay_kmax != 0;
+  const bool plain_model = table_delay && P.delay_kmax + 2 <= 256 && P.silent_mask == 0;
+  if (P.record_rs || P.resumable) return FX_NONE;
+  if (P.L.queue_scan == 2 && plain_model && memcmp(&P.L, &kDefault4, sizeof(Layout)) == 0) return FX_DEFAULT4;
+  if (P.L.queue_scan == 3 && plain_model && memcmp(&P.L, &kPart7, sizeof(Layout)) == 0) return FX_PART7;
+  if (P.L.queue_scan == 3 && table_delay && memcmp(&P.L, &kCommittee64, sizeof(Layout)) == 0) return FX_COMMITTEE64;
+  return FX_NONE;
 }
 
 static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* last_states, uint32_t* lc_round,
@@ -93,6 +99,13 @@ int hostcore_setup_info(const lbft_config* c, uint32_t* out6) {
   out6[4] = hs.params.L.payload_cap;
   out6[5] = hs.params.L.total_words;
   return LBFT_OK;
+}
+
+// Which compile-time-layout instantiation (sim_params.h FX_*) hostcore_run takes for this configuration; 0 = generic.
+int hostcore_fixed_shape(const lbft_config* c) {
+  HostSetup hs;
+  if (!hs.build(*c)) { g_err = hs.error; return -1; }
+  return getenv("HOSTCORE_NO_FIXED") ? (int)FX_NONE : fixed_selected(hs.params);
 }
 
 // Same outputs as the product's lbft_* getters; chain_out (optional) receives, per instance,
@@ -177,7 +190,10 @@ static int run_impl(const lbft_config* c, uint32_t* commit_counts, uint64_t* las
                               : run_all<NMAX, QS, false, true>(P, state, P.zig_x, P.zig_f))                          \
                : (P.record_rs ? run_all<NMAX, QS, true, false>(P, state, P.zig_x, P.zig_f)                          \
                               : run_all<NMAX, QS, false, false>(P, state, P.zig_x, P.zig_f)))
-  if (fixed_selected(P) && !getenv("HOSTCORE_NO_FIXED")) run_all_fixed(P, state, P.zig_x, P.zig_f);
+  const int fx = getenv("HOSTCORE_NO_FIXED") ? (int)FX_NONE : fixed_selected(P);
+  if (fx == FX_DEFAULT4) run_all_fx<16, 2, FX_DEFAULT4>(P, state, P.zig_x, P.zig_f);
+  else if (fx == FX_PART7) run_all_fx<16, 3, FX_PART7>(P, state, P.zig_x, P.zig_f);
+  else if (fx == FX_COMMITTEE64) run_all_fx<64, 3, FX_COMMITTEE64>(P, state, P.zig_x, P.zig_f);
   else if (P.L.queue_scan == 2) RUN(16, 2);
   else if (P.L.queue_scan == 1) RUN(16, 1);
   else if (P.L.queue_scan == 3) {

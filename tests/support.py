@@ -196,6 +196,11 @@ class HostCore:
             raise RuntimeError(self.lib.hostcore_last_error().decode())
         return dict(zip(("delay_kmax", "queue_scan", "round_cap", "queue_cap", "payload_cap", "words"), out.tolist()))
 
+    def fixed_shape(self, num_nodes, max_clock=1000, **kw):
+        """sim_params.h FX_* of the instantiation `run` takes for this configuration (0: the generic one)."""
+        cfg, keep = make_config([1], num_nodes, max_clock, **kw)
+        return self.lib.hostcore_fixed_shape(ctypes.byref(cfg))
+
     def run(self, seeds, num_nodes, max_clock=1000, **kw):
         cfg, keep = make_config(seeds, num_nodes, max_clock, **kw)
         I = cfg.num_instances

@@ -16,6 +16,8 @@ def test_automatic_choice(monkeypatch):
     from tests.test_gpu_parity import make_sim
     picks = {}
     for name, count, nodes, kw in (("config2", 1024, 4, {}), ("config3", 65536, 4, {}), ("config5", 16384, 7, {}),
+                                   ("config5p", 16384, 7, {"partition_windows": 4, "partition_max_len": 150}),
+                                   ("mid7", 8192, 7, {}), ("full7", 65536, 7, {}), ("big64", 8192, 64, {}),
                                    ("small64", 64, 64, {}), ("resumable", 64, 4, {"resumable": True}),
                                    ("recording", 64, 7, {"record_round_switches": True}), ("mid4", 8192, 4, {}),
                                    ("long7", 64, 7, {"max_clock": 20000})):
@@ -23,11 +25,16 @@ def test_automatic_choice(monkeypatch):
         sim = make_sim(np.arange(1, count + 1, dtype=np.uint64), nodes, **kw).create(max_clock)
         picks[name] = sim.kernel_info()
         sim.close()
-    assert picks["config2"] == "lbft_wide_kernel<16,2,true,32,false>"      # a warp per instance, whole instance in shared memory
-    assert picks["config3"] == picks["mid4"] == "lbft_event_loop_kernel<16,2,true,false,false,false,false,32>"
-    assert picks["config5"] == "lbft_wide_kernel<16,2,false,8,false>"      # 8 lanes per instance, four instances per warp
-    assert picks["small64"] == "lbft_wide_kernel<64,3,false,32,false>"     # (8 192 x 64 selects <64,3,false,8,false>)
-    assert picks["long7"] == "lbft_wide_kernel<16,0,false,32,false>"       # beyond the 14-bit times of the compact queue
+    # <NMAX, QMODE, SMEM, lanes per instance, EP, FX> / <NMAX, QMODE, FX, REC, RES, EP, TDS, instances per warp tile>
+    assert picks["config2"] == "lbft_wide_kernel<16,2,true,32,false,0>"    # a warp per instance, whole instance in shared memory
+    assert picks["config3"] == picks["mid4"] == "lbft_event_loop_kernel<16,2,1,false,false,false,false,32>"
+    assert picks["config5"] == "lbft_event_loop_kernel<16,3,0,false,false,false,false,8>"  # one wave of 8-instance warp tiles
+    assert picks["config5p"] == "lbft_event_loop_kernel<16,3,2,false,false,false,false,8>"  # ... BASELINE configs[4]: its compile-time shape
+    assert picks["mid7"] == "lbft_wide_kernel<16,2,false,8,false,0>"       # 8 lanes per instance, four instances per warp
+    assert picks["full7"] == "lbft_event_loop_kernel<16,3,0,false,false,false,false,32>"
+    assert picks["small64"] == "lbft_wide_kernel<64,3,false,32,false,0>"
+    assert picks["big64"] == "lbft_wide_kernel<64,3,false,8,false,3>"      # BASELINE configs[3]: compile-time shape, 8 lanes per instance
+    assert picks["long7"] == "lbft_wide_kernel<16,0,false,32,false,0>"     # beyond the 14-bit times of the compact queue
     assert picks["resumable"].startswith("lbft_event_loop_kernel") and picks["recording"].startswith("lbft_event_loop_kernel")
 
 

@@ -94,3 +94,39 @@ def test_epoch_end_stalls_like_the_reference_semantics(oracle, hostcore):
     h = hostcore.run(seeds, 4, 1000, commands_per_epoch=5)
     assert (h.status == 33).all()
     assert_same(o, h, "epoch stall")
+
+
+W64 = [1 + (i % 3) for i in range(64)]
+SILENT64 = [1 if i % 3 == 0 and i <= 60 else 0 for i in range(64)]
+
+
+def test_compile_time_shapes_match_the_oracle_and_the_generic_instantiation(oracle, hostcore, monkeypatch):
+    """The instantiations with a compile-time layout (sim_params.h FX_*: BASELINE configs 1-3, configs[4], configs[3])
+    are selected for exactly those shapes and compute what the oracle and the generic instantiation compute."""
+    shapes = [
+        (1, 4, 24, {}),                                                              # FX_DEFAULT4
+        (2, 7, 24, {"partition_windows": 4, "partition_max_len": 150}),              # FX_PART7 (BASELINE configs[4])
+        (3, 64, 2, {"voting_rights": W64, "silent": SILENT64}),                      # FX_COMMITTEE64 (BASELINE configs[3])
+        (3, 64, 1, {}),                                                              # ... voting rights / silent nodes are run-time
+    ]
+    # (the layout of a handle depends on the kernel family the host picks for the batch size: the seven-author shape is the
+    # thread kernel's, which 16 384 instances select on their own — tests/test_gpu_wide.py — and small batches only when asked)
+    monkeypatch.setenv("LBFT_FORCE_KERNEL", "thread")
+    for fx, nodes, count, kw in shapes:
+        assert hostcore.fixed_shape(nodes, 1000, **kw) == fx
+        seeds = np.arange(31000, 31000 + count, dtype=np.uint64)
+        o, h = oracle.run(seeds, nodes, 1000, **kw), hostcore.run(seeds, nodes, 1000, **kw)
+        assert (h.status == 1).all()
+        assert_same(o, h, "compile-time shape %d" % fx)
+        monkeypatch.setenv("HOSTCORE_NO_FIXED", "1")
+        g = hostcore.run(seeds, nodes, 1000, **kw)
+        monkeypatch.delenv("HOSTCORE_NO_FIXED")
+        assert_same(g, h, "generic vs compile-time shape %d" % fx)
+        np.testing.assert_array_equal(g.counters, h.counters)
+    # neighbouring configurations stay generic
+    assert hostcore.fixed_shape(7, 1000) == 0                                                   # no partition windows
+    assert hostcore.fixed_shape(7, 1200, partition_windows=4, partition_max_len=150) == 0     # another horizon
+    assert hostcore.fixed_shape(7, 1000, partition_windows=4, partition_max_len=150, delay_kind=1, delay_lo=5, delay_hi=15) == 0
+    assert hostcore.fixed_shape(7, 1000, partition_windows=4, partition_max_len=150, silent=[1, 0, 0, 0, 0, 0, 0]) == 0
+    assert hostcore.fixed_shape(48, 1000) == 0
+    assert hostcore.fixed_shape(4, 1000, flags=1) == 0                                          # recording
