@@ -245,10 +245,13 @@ struct HostSetup {
       if (qscan == 2 && qcap > (use_wide ? 1024u : 64u)) qscan = N <= 5 ? 1u : (c.max_clock <= 4095 ? 3u : 0u);
     }
     p.L = make_layout(N, rcap, qcap, pcap, c.partition_windows, qscan, (uint32_t)c.max_clock, p.record_rs != 0, p.resumable != 0, epochs, tds);
-    if (!use_wide && want_tile != 32 && ((qscan == 3 && (want_tile == 8 || N <= 16)) || (qscan == 2 && want_tile == 8)) && !modes && !tds && epochs == 1)
+    // (calendar queue: the sparse-tile kernels keep the occupancy words of their instances in shared memory, sim_core.cuh KS —
+    // ((max_clock + 8) / 8) x tile words per warp, 14 warps per SM: horizons up to ~3 500 ms at 8 per warp, ~1 750 at 16)
+    const bool ks_fits = (uint64_t)(((uint32_t)c.max_clock + 8) / 8) * want_tile <= 3584;
+    if (!use_wide && want_tile != 32 && ((qscan == 3 && ks_fits && (want_tile == 8 || N <= 16)) || (qscan == 2 && want_tile == 8)) && !modes && !tds && epochs == 1)
       tile_stride = want_tile;
-    // wide kernel: the whole instance lives in shared memory when four 128-thread blocks (128 / group instances each) of it
-    // fit on an SM
+    // wide kernel: the whole instance lives in shared memory when the instances of 16 resident warps (32 / group each) fit on
+    // an SM
     {
       const size_t bytes = sizeof(uint32_t) * (size_t)p.L.total_words + 6u * (size_t)qcap + 1024u;
       wide_smem = use_wide && qscan == 2 && epochs == 1 && bytes * (128u / wide_group) <= 56u * 1024u;

@@ -13,6 +13,16 @@
 
 namespace lbft {
 
+#ifndef LBFT_NO_KS
+#define LBFT_NO_KS 0  // A/B switch: 1 keeps the calendar's occupancy words in the instance's HBM block everywhere
+#endif
+// The wide kernels keep them in HBM: measured (profiles/r2n_ab_ks.txt) 8 192 x 64 on 8 lanes per instance 879 ms with the words in
+// shared memory against 858 ms without (1 024 x 64 on a warp per instance: 313 vs 317 ms) — the words are L1-resident there
+// anyway; the sparse-tile thread kernel gains 7.7 % (16 384 x 7: 42.4 vs 45.9 ms).
+#ifndef LBFT_WIDE_KS
+#define LBFT_WIDE_KS 0
+#endif
+LBFT_LAYOUT_FN uint32_t calendar_kmask_words(const Layout& L) { return (L.cal_times + 7) / 8; }
 constexpr uint32_t kThrSmem = 256;  // doubles: delay thresholds held in shared memory when they fit
 
 // Launch shapes of the thread-per-instance kernel.  QMODE 0/1/3: one-warp blocks, 14 resident per SM (2 048 tiles of a
@@ -44,6 +54,7 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
   __shared__ double s_zf[257];
   __shared__ double s_thr[kThrSmem];  // delay thresholds (same scattered access pattern), when they fit
   extern __shared__ uint32_t s_queue[];  // QMODE 2: per warp [queue_cap][32] u32 keys, then [queue_cap][32] u16 payload words
+                                         // QMODE 3, sparse tiles: per warp [kmask words][TILE] calendar occupancy words
   for (int i = threadIdx.x; i < 257; i += blockDim.x) {
     s_zx[i] = P.zig_x[i];
     s_zf[i] = P.zig_f[i];
@@ -66,7 +77,11 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
     sk = base + lane;
     sd = reinterpret_cast<uint16_t*>(base + qcap * 32) + lane;
   }
-  Core<TileMem<TILE>, NMAX, QMODE, FX, REC, RES, 1, EP, TDS> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  // sparse tiles over the calendar queue: the kind-occupancy words of the tile's instances in shared memory, a column per
+  // lane (sim_core.cuh KS; the host only selects sparse tiles when 14 warps' worth fits, host_setup.hpp)
+  constexpr bool KS = QMODE == 3 && TILE < 32 && !LBFT_NO_KS;
+  Core<TileMem<TILE>, NMAX, QMODE, FX, REC, RES, 1, EP, TDS, KS> core(P, mem, s_zx, s_zf, thr_fits ? s_thr : P.delay_thr, sk, sd);
+  if (KS) core.km = s_queue + (size_t)(threadIdx.x >> 5) * calendar_kmask_words(FX ? fixed_layout(FX) : P.L) * TILE + lane;
   if (RES && (P.run_flags & 1u)) core.restore_regs();  // a later lbft_run_until: continue where the last launch stopped
   else core.init(P.seeds[inst]);
   core.run();
@@ -75,15 +90,20 @@ __global__ void __launch_bounds__(LaunchShape<QMODE>::kThreads, LaunchShape<QMOD
 }
 
 // ---- a group of G lanes per instance ("wide") ---------------------------------------------------------------------
-// kWideWarps warps per block, 32 / G instances per warp (instance = global group index; the hardware block scheduler hands
+// wide_warps(G) warps per block, 32 / G instances per warp (instance = global group index; the hardware block scheduler hands
 // out the next block as soon as one retires, which is the work queue SURVEY §8e asks for).  The state of an instance is one
 // contiguous extent (TileMem<1>: stride 1), tables are read through L1 (every lane of a group reads the same element), the
 // shared-memory queue of QMODE 2 and the fan-out scratch are per group.
-constexpr int kWideWarps = 4;
-#ifndef LBFT_WIDE_BLOCKS
-#define LBFT_WIDE_BLOCKS 4  // blocks per SM the register allocation is bounded for: 4 -> 16 warps per SM, <= 128 registers
+// Warps per block: four when a warp carries several instances; ONE when a warp is an instance (G = 32): a block is then a
+// single instance, its index arithmetic folds away (5 192 instead of 5 600 SASS instructions) and blocks retire one by one —
+// measured (profiles/r2p_ab_wide_warps.txt) 1 024 x 4: 2.48 ms against 3.81 with four-warp blocks, a lone instance 3.66 against
+// 4.44 ms; 8 lanes per instance (8 192 x 64) is indifferent: 838 / 842 / 840 ms for 4 / 2 / 1 warps.
+#ifndef LBFT_WIDE_WARPS
+#define LBFT_WIDE_WARPS 4  // (blocks of the G < 32 kernels)
 #endif
-constexpr int kWideBlocksPerSm = LBFT_WIDE_BLOCKS;
+LBFT_LAYOUT_FN int wide_warps(int g) { return g == 32 ? 1 : LBFT_WIDE_WARPS; }
+// blocks per SM the register allocation is bounded for: 16 warps per SM, <= 128 registers
+LBFT_LAYOUT_FN int wide_blocks_per_sm(int g) { return 16 / wide_warps(g); }
 
 // Shared memory of one group: [scratch][QMODE 2: queue keys, queue payload halves][SMEM: the instance state]
 LBFT_LAYOUT_FN uint32_t wide_scratch_words() { return (uint32_t)((sizeof(WideScratch) + 7) / 8 * 2); }
@@ -91,15 +111,16 @@ LBFT_LAYOUT_FN uint32_t wide_queue_words(uint32_t queue_cap, int qmode) {
   return qmode == 2 ? ((queue_cap + (queue_cap + 1) / 2 + 1) & ~1u) : 0u;  // even: what follows holds 64-bit entries
 }
 LBFT_LAYOUT_FN uint32_t wide_smem_words_per_group(const Layout& L, int qmode, bool smem_state) {
-  return wide_scratch_words() + wide_queue_words(L.queue_cap, qmode) + (smem_state ? ((L.total_words + 1) & ~1u) : 0u);
+  return wide_scratch_words() + wide_queue_words(L.queue_cap, qmode) + (smem_state ? ((L.total_words + 1) & ~1u) : 0u) +
+         (qmode == 3 && LBFT_WIDE_KS ? ((calendar_kmask_words(L) + 1) & ~1u) : 0u);  // QMODE 3: the calendar's occupancy words (sim_core.cuh KS)
 }
 
 // SMEM: the instance's state words live in shared memory for the whole run; only the chain table (and the epoch table) is
 // copied to the instance's global extent at the end, for lbft_commit_log / lbft_commit_logs.
 template <int NMAX, int QMODE, bool SMEM, int G, bool EP = false, int FX = FX_NONE>
-__global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(wide_warps(G) * 32, wide_blocks_per_sm(G)) lbft_wide_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(8) uint32_t s_wide[];
-  constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
+  constexpr uint32_t kPerBlock = wide_warps(G) * 32 / G;
   const uint32_t grp = threadIdx.x / G, wl = threadIdx.x % G;
   const uint32_t inst = blockIdx.x * kPerBlock + grp;
   if (inst >= P.num_instances) return;  // whole groups leave together: everything below is group-uniform
@@ -111,7 +132,9 @@ __global__ void __launch_bounds__(kWideWarps * 32, kWideBlocksPerSm) lbft_wide_k
   uint32_t* gstate = P.state + (size_t)inst * KL.total_words;
   uint32_t* state = SMEM ? sk + wide_queue_words(KL.queue_cap, QMODE) : gstate;
   TileMem<1> mem{state, 0};
-  Core<TileMem<1>, NMAX, QMODE, FX, false, false, G, EP> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
+  constexpr bool KS = QMODE == 3 && LBFT_WIDE_KS;
+  Core<TileMem<1>, NMAX, QMODE, FX, false, false, G, EP, false, KS> core(P, mem, P.zig_x, P.zig_f, P.delay_thr, sk, sd);
+  if (KS) core.km = base + wide_scratch_words();  // (QMODE 3 has no shared-memory queue and no shared-memory state: the words follow the scratch)
   core.wl = wl;
   core.gm = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(G - 1)));
   core.ws = ws;
@@ -152,7 +175,9 @@ template <int NMAX, int QM, int TILE, int FX = FX_NONE>
 inline cudaError_t launch_sparse_tiles(const Params& P, cudaStream_t stream) {
   constexpr int T = LaunchShape<QM>::kThreads;
   const uint32_t tiles = (P.num_instances + TILE - 1) / TILE, blocks = (tiles * 32 + T - 1) / T;
-  const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2) : 0;
+  const size_t dyn = QM == 2 ? (size_t)(T / 32) * P.L.queue_cap * (32 * 4 + 32 * 2)
+                             : (size_t)(T / 32) * calendar_kmask_words(P.L) * TILE * sizeof(uint32_t);  // (QMODE 3: sim_core.cuh KS)
+  if (dyn > 48 * 1024) return cudaErrorInvalidValue;  // (the host keeps sparse tiles to horizons whose occupancy words fit)
   lbft_event_loop_kernel<NMAX, QM, FX, false, false, false, false, TILE><<<blocks, T, dyn, stream>>>(P);
   return cudaGetLastError();
 }
@@ -176,7 +201,7 @@ inline cudaError_t launch_thread_variants(const KernelSel& k, const Params& P, c
 
 template <int NMAX, int QM, bool SMEM, int G, bool EP, int FX = FX_NONE>
 inline cudaError_t launch_wide_variant(const Params& P, cudaStream_t stream) {
-  constexpr uint32_t kPerBlock = kWideWarps * 32 / G;
+  constexpr uint32_t kPerBlock = wide_warps(G) * 32 / G;
   const uint32_t blocks = (P.num_instances + kPerBlock - 1) / kPerBlock;
   const size_t dyn = (size_t)kPerBlock * wide_smem_words_per_group(P.L, QM, SMEM) * sizeof(uint32_t);
   static size_t attr_set = 48 * 1024;  // (per instantiation; two threads racing set the same or a larger value)
@@ -185,7 +210,7 @@ inline cudaError_t launch_wide_variant(const Params& P, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_set = dyn;
   }
-  lbft_wide_kernel<NMAX, QM, SMEM, G, EP, FX><<<blocks, kWideWarps * 32, dyn, stream>>>(P);
+  lbft_wide_kernel<NMAX, QM, SMEM, G, EP, FX><<<blocks, wide_warps(G) * 32, dyn, stream>>>(P);
   return cudaGetLastError();
 }
 // the lanes-per-instance / epoch dimensions of an instantiation family (the host only selects these combinations)

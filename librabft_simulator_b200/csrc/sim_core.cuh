@@ -278,6 +278,30 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
   return flag | (int64_t)v;
 }
 
+// Partition plan (EXTENSION): the windows open at `clock` and the next clock at which that set changes.
+// Out of line: it runs at most twice per window per run, and inlined into every send site it costs the kernels that never
+// see a partition ~5 % of their code.  packed: the open windows' author masks themselves, 16 bits per window (<= 4 windows,
+// <= 16 authors), instead of a bit per open window.
+struct PartitionSpan {
+  uint64_t open;
+  int32_t until;
+};
+template <class Mem>
+LBFT_COLD PartitionSpan partition_span(Mem m, uint32_t part_base, uint32_t windows, int32_t clock, bool packed) {
+  PartitionSpan sp;
+  sp.open = 0;
+  sp.until = 0x7fffffff;
+  for (uint32_t k = 0; k < windows; k++) {
+    const int32_t t0 = (int32_t)m.ld(part_base + 4 * k), t1 = (int32_t)m.ld(part_base + 4 * k + 1);
+    if (clock < t0) { if (t0 < sp.until) sp.until = t0; }
+    else if (clock < t1) {
+      sp.open |= packed ? (uint64_t)(m.ld(part_base + 4 * k + 2) & 0xffffu) << (16 * k) : 1ULL << k;
+      if (t1 < sp.until) sp.until = t1;
+    }
+  }
+  return sp;
+}
+
 // QMODE: 0 binary heap (3-word entries, HBM) | 1 scan queue, 64-bit keys in HBM | 2 scan queue, 32-bit keys +
 // 16-bit payload words in shared memory (small committees, short horizons) | 3 calendar queue in HBM
 // FX (FIXED = FX != 0): the layout is the compile-time constant fixed_layout(FX) (sim_params.h: the default four-author
@@ -304,9 +328,14 @@ LBFT_COLD int64_t delay_via_exp(double mu, double sigma, double z) {  // bit 62 
 // and the response's records are inserted by the requester (what data_sync.rs:183-240 is written for), instead of the
 // reference simulator's dispatch to the requester itself (simulator.rs:446).  An opt-in NON-PARITY
 // variant; plain thread-per-instance kernels only.
+// KS: (QMODE 3) the calendar's kind-occupancy words live in shared memory (`km`) for the whole run instead of the instance's
+// HBM block: the first hop of every pop and the occupancy test of every push become shared-memory accesses, and a push
+// into an empty list issues no load at all.  Sparse-tile thread kernels and the wide kernels (a handful of instances per
+// warp: (max_clock + 8) / 8 words each fit); plain one-shot runs only (nothing is kept between launches).
 template <class Mem, int NMAX, int QMODE, int FX = 0, bool REC = false, bool RES = false, int G = 1, bool EP = false,
-          bool TDS = false>
+          bool TDS = false, bool KS = false>
 struct Core {
+  static_assert(!KS || (QMODE == 3 && !RES), "shared-memory occupancy words: calendar queue, one-shot runs");
   static constexpr bool FIXED = FX != FX_NONE;                               // compile-time layout, reference delay model
   static constexpr bool MAY_SILENT = FX == FX_NONE || FX == FX_COMMITTEE64;  // silent nodes (extension D.2) reachable
   static_assert(!(FIXED && EP), "the compile-time layout is single-epoch");
@@ -329,6 +358,13 @@ struct Core {
   // dropped at a stop must be the one the reference drops).
   static constexpr bool ELIDE = !(REC || RES);
   static constexpr int S = Mem::STRIDE;
+  static constexpr int KSTR = WIDE ? 1 : S;  // KS: stride between this instance's occupancy words (a column per lane / contiguous)
+  uint32_t* km = nullptr;                    // KS: this instance's occupancy words in shared memory
+  LBFT_HD uint32_t km_ld(uint32_t w) const { return KS ? km[w * KSTR] : m.ld(L.cal_kmask + w); }
+  LBFT_HD void km_st(uint32_t w, uint32_t v) const {
+    if (KS) km[w * KSTR] = v;
+    else m.st(L.cal_kmask + w, v);
+  }
   const Params& P;
   const Layout L;
   Mem m;
@@ -573,15 +609,15 @@ struct Core {
       if (cal_free != PAY_NONE) { e = cal_free; cal_free = m.ld(L.heap_time + e); }
       else e = cal_next++;
       m.st(L.heap_key + e, data);
-      const uint32_t t = (uint32_t)time, kw = L.cal_kmask + (t >> 3), sh = (t & 7) * 4 + kind, hw = L.cal_ht + t * 4 + kind;
-      uint32_t occ = m.ld(kw);
+      const uint32_t t = (uint32_t)time, kw = t >> 3, sh = (t & 7) * 4 + kind, hw = L.cal_ht + t * 4 + kind;
+      uint32_t occ = km_ld(kw);
       if ((occ >> sh) & 1) {
         uint32_t ht = m.ld(hw);
         m.st(L.heap_time + (ht >> 16), e);       // old tail -> e
         m.st(hw, (ht & 0xffffu) | (e << 16));
       } else {
         m.st(hw, e | (e << 16));
-        m.st(kw, occ | (1u << sh));
+        km_st(kw, occ | (1u << sh));
       }
       qsize++;
       if (qsize > max_queue) max_queue = qsize;
@@ -623,12 +659,12 @@ struct Core {
   LBFT_HD void pop_event(int32_t& time, uint32_t& kind, uint32_t& data) {
     if (QMODE == 3) {
       // advance to the first time slot with a pending list (pushes never go below the current slot)
-      uint32_t kw = L.cal_kmask + (cal_t >> 3);
-      uint32_t occ = m.ld(kw) >> ((cal_t & 7) * 4);
+      uint32_t kw = cal_t >> 3;
+      uint32_t occ = km_ld(kw) >> ((cal_t & 7) * 4);
       while (occ == 0) {
         cal_t = (cal_t | 7) + 1;
         kw++;
-        occ = m.ld(kw);
+        occ = km_ld(kw);
       }
       while ((occ & 15u) == 0) { occ >>= 4; cal_t++; }
       const uint32_t nib = occ & 15u;
@@ -636,7 +672,7 @@ struct Core {
       const uint32_t hw = L.cal_ht + cal_t * 4 + kind;
       const uint32_t ht = m.ld(hw), e = ht & 0xffffu;
       data = m.ld(L.heap_key + e);
-      if (e == (ht >> 16)) m.st(kw, m.ld(kw) & ~(1u << ((cal_t & 7) * 4 + kind)));  // list became empty
+      if (e == (ht >> 16)) km_st(kw, km_ld(kw) & ~(1u << ((cal_t & 7) * 4 + kind)));  // list became empty
       else m.st(hw, (ht & 0xffff0000u) | m.ld(L.heap_time + e));
       m.st(L.heap_time + e, cal_free);
       cal_free = e;
@@ -1275,17 +1311,9 @@ struct Core {
   LBFT_HD bool packed_plan() const { return NMAX <= 16 && L.part_windows <= 4; }
   LBFT_HD bool partitioned(uint32_t a, uint32_t b2) {  // EXTENSION
     if (clock >= part_until) {
-      part_open = 0;
-      int32_t until = 0x7fffffff;
-      for (uint32_t k = 0; k < L.part_windows; k++) {
-        const int32_t t0 = (int32_t)m.ld(L.part_base + 4 * k), t1 = (int32_t)m.ld(L.part_base + 4 * k + 1);
-        if (clock < t0) { if (t0 < until) until = t0; }
-        else if (clock < t1) {
-          part_open |= packed_plan() ? (uint64_t)(m.ld(L.part_base + 4 * k + 2) & 0xffffu) << (16 * k) : 1ULL << k;
-          if (t1 < until) until = t1;
-        }
-      }
-      part_until = until;
+      const PartitionSpan sp = partition_span(m, L.part_base, L.part_windows, clock, packed_plan());
+      part_open = sp.open;
+      part_until = sp.until;
     }
     if (packed_plan()) return (((part_open >> a) ^ (part_open >> b2)) & 0x0001000100010001ULL) != 0;
     for (uint64_t open = part_open; open; open &= open - 1) {
@@ -1346,7 +1374,7 @@ struct Core {
     }
     // (table clears are split over the lanes of the group; G == 1: wl == 0, the plain loops)
     if (QMODE == 3)
-      for (uint32_t w = wl; w < (L.cal_times + 7) / 8; w += G) m.st(L.cal_kmask + w, 0);
+      for (uint32_t w = wl; w < (L.cal_times + 7) / 8; w += G) km_st(w, 0);
     for (uint32_t w = wl; w < N * L.node_words; w += G) m.st(L.node_base + w, 0);
     for (uint32_t w = wl; w < 2 * L.rset_words; w += G) m.st(L.created_base + w, 0);
     if (multi())

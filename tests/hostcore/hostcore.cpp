@@ -49,7 +49,11 @@ static void run_all_fx(const Params& P, std::vector<uint32_t>& state, const doub
     TileMem<32> mem{state.data() + (size_t)tile * P.L.total_words * 32, lane};
     std::vector<uint32_t> sk(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);
     std::vector<uint16_t> sd(QMODE == 2 ? (size_t)P.L.queue_cap * 32 : 1);
-    Core<TileMem<32>, NMAX, QMODE, FX> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
+    // (calendar queue: with the occupancy words in a stand-in for shared memory, as the sparse-tile / wide kernels hold them)
+    constexpr bool KS = QMODE == 3;
+    std::vector<uint32_t> km(KS ? (size_t)((P.L.cal_times + 7) / 8) * 32 : 1);
+    Core<TileMem<32>, NMAX, QMODE, FX, false, false, 1, false, false, KS> core(P, mem, zx, zf, P.delay_thr, sk.data() + lane, sd.data() + lane);
+    core.km = km.data() + lane;
     core.init(P.seeds[inst]);
     core.run();
     core.finalize(inst);
