@@ -44,6 +44,14 @@
 #include <cmath>
 #endif
 
+// A/B switches of two exact optimisations (profiles/r2r_ab_exact.txt): see enqueue_network_event and st_u16.
+#ifndef LBFT_ELIDE_SILENT
+#define LBFT_ELIDE_SILENT 1
+#endif
+#ifndef LBFT_ST16
+#define LBFT_ST16 1
+#endif
+
 namespace lbft {
 
 // Status bits — keep in sync with include/lbft.h (static_asserted in lbft_api.cu).
@@ -479,7 +487,13 @@ struct Core {
     if (NMAX > 32) p[S] = (uint32_t)((uint64_t)v >> 32);
   }
   LBFT_HD static uint32_t ld_u16(const uint32_t* p, uint32_t i) { return (p[(i >> 1) * S] >> (16 * (i & 1))) & 0xffffu; }
+  // (a 16-bit store: the read-modify-write of the containing word put a dependent load — a DRAM miss in the 64-author
+  // configuration — in front of every accepted timeout)
   LBFT_HD static void st_u16(uint32_t* p, uint32_t i, uint32_t v) {
+    if (LBFT_ST16) {
+      reinterpret_cast<uint16_t*>(p + (i >> 1) * S)[i & 1] = (uint16_t)v;  // little-endian halves, as ld_u16 reads them
+      return;
+    }
     uint32_t x = p[(i >> 1) * S];
     uint32_t sh = 16 * (i & 1);
     p[(i >> 1) * S] = (x & ~(0xffffu << sh)) | (v << sh);
@@ -597,9 +611,10 @@ struct Core {
   // schedule_event (simulator.rs:252-264).  Events beyond max_clock can never be popped before the
   // loop ends (:389-391): they consume their creation stamp and are dropped.  Returns true if queued.
   // `data` = receiver | sender << 8 | slot << 16.
+  static constexpr uint32_t kStampLimit = QMODE == 2 ? (1u << 16) : (QMODE == 1 ? (1u << 22) : (QMODE == 3 ? 0xfffffff0u : (1u << 30)));  // width of the stamp field of the queue's keys
   LBFT_HD bool push_event(int32_t time, uint32_t kind, uint32_t data) {
     uint32_t st = stamp++;
-    if (stamp >= (QMODE == 2 ? (1u << 16) : (QMODE == 1 ? (1u << 22) : (QMODE == 3 ? 0xfffffff0u : (1u << 30))))) status |= ST_QUEUE_OVERFLOW;
+    if (stamp >= kStampLimit) status |= ST_QUEUE_OVERFLOW;
     if (time > P.max_clock) return false;
     if (qsize >= L.queue_cap) { status |= ST_QUEUE_OVERFLOW; return false; }
     if (QMODE == 3) {
@@ -1330,6 +1345,22 @@ struct Core {
     int32_t t = clock + delay;
     if (L.part_windows && partitioned(receiver, sender)) {
       stamp++;
+      return false;
+    }
+    // EXTENSION D.2, exact elision: a notification addressed to a silent node, or a request whose addressee is silent, is
+    // dropped by the loop right after its pop with no effect but the event counters (run(): the clock it advances is
+    // overwritten by the next live event before anything reads it).  Account for the pop here — it is certain: every queued
+    // event up to max_clock is popped before a one-shot run ends — and keep the event, a third of the 64-author
+    // configuration's traffic, out of the queue and out of the snapshot's reference count.  It still takes its creation
+    // stamp and its delay draw.  Not while recording / resumable / true-data-sync (every pop is observable there).
+    if (LBFT_ELIDE_SILENT && ELIDE && !TDS && MAY_SILENT && P.silent_mask && kind != EV_RESPONSE &&
+        ((P.silent_mask >> (kind == EV_NOTIFY ? receiver : sender)) & 1)) {
+      stamp++;
+      if (stamp >= kStampLimit) status |= ST_QUEUE_OVERFLOW;
+      if (t <= P.max_clock) {
+        if (kind == EV_NOTIFY) proc0++;
+        else proc1++;
+      }
       return false;
     }
     return push_event(t, kind, receiver | (sender << 8) | (slot << 16));
