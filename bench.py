@@ -305,9 +305,8 @@ def measure_side_config(cfg_id, device, steps=2, warmup=1):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_rounds = 0.0
-    for s in range(steps):
-        sim.set_seeds(step_seeds(cfg, s, 0, I))
-        e2e_rounds += float(sim.run(strict=False).active_rounds.sum())
+    for r in sim.run_stream((step_seeds(cfg, s, 0, I) for s in range(steps)), strict=False):
+        e2e_rounds += float(r.active_rounds.sum())
     e2e_s = time.perf_counter() - t0
     kms, rounds, res, seeds = [], 0.0, None, None
     for s in range(steps):
@@ -426,9 +425,10 @@ def main():
     e2e_rounds = 0.0
     barrier()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        sharded.set_seeds(job_seeds(s))                   # host array (pinned staging inside the library)
-        res = sharded.run(strict=False)                   # H2D seeds + kernel + D2H summaries into caller arrays + all-gather
+    # One run is always in flight (ShardedBatchSimulator.run_stream = lbft_run_async / lbft_wait): every step copies its seeds
+    # host->device from the pinned staging buffer and its summaries device->host into caller-owned arrays, and is
+    # all-gathered; the staging of step k + 1 and the host-side copies of step k overlap a kernel.
+    for res in sharded.run_stream((job_seeds(s) for s in range(args.steps)), strict=False):
         e2e_rounds += float(res.local.active_rounds.sum())
     barrier()
     e2e_seconds = time.perf_counter() - t0
@@ -474,7 +474,8 @@ def main():
                                       "state keys, rounds} per step" % world},
             "e2e": {"value": e2e_rounds / e2e_seconds, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": 1e3 * e2e_seconds / args.steps,
-                    "returns": "commit counts [I][N], state keys [I][N], rounds [I], status [I] in caller-owned host arrays"},
+                    "returns": "commit counts [I][N], state keys [I][N], rounds [I], status [I] in caller-owned host arrays",
+                    "pipeline": "run_stream: one run in flight per GPU (lbft_run_async / lbft_wait, double-buffered pinned staging)"},
             "gpu_launches": args.steps * 2,
             "roofline": roofline_block(args.config, cfg, per_gpu, last.counters, k_ms, kernel),
             "clocks": clocks,

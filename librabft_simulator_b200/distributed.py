@@ -44,6 +44,8 @@ class ShardedResult:
         self._shape, self._decoded = (instances_per_rank, num_nodes), None
 
     def _decode(self):
+        if self._decoded is None and self.block is None:  # one rank: the whole job is this rank's shard
+            self._decoded = (self.local.commit_counts, self.local.last_committed_states, self.local.active_rounds)
         if self._decoded is None:
             I, N = self._shape
             b = self.block.detach().cpu().numpy() if hasattr(self.block, "detach") else np.asarray(self.block)
@@ -120,7 +122,9 @@ class ShardedBatchSimulator:
         returns.  On a CUDA backend the source is the device-resident summary block; otherwise the host arrays of
         ``local_result`` packed the same way.  Returns the gathered ``[world, bytes]`` block (see ``ShardedResult``)."""
         import torch
-        on_device = self.dist is not None and self.world > 1 and self.dist.get_backend() == "nccl"
+        if self.world == 1 or self.dist is None:
+            return None  # nothing to gather: ShardedResult reads this rank's arrays
+        on_device = self._gathers_on_device()
         if on_device:
             block = self._device_summary()
         else:
@@ -133,10 +137,47 @@ class ShardedBatchSimulator:
             torch.cuda.current_stream(allb.device).synchronize()  # the results are complete (and the sources free) on return
         return allb
 
+    def _gathers_on_device(self):
+        return self.dist is not None and self.world > 1 and self.dist.get_backend() == "nccl"
+
     def run(self, strict=True):
         """``lbft_run`` on this rank's shard (host seeds in, host summaries out) + the all-gather."""
         res = self.local.run(strict=strict)
         return ShardedResult(res, self.gather(res), self.hi - self.lo, self.num_nodes, self.lo, self.hi)
+
+    def run_stream(self, batches, strict=True):
+        """A sequence of whole-job seed batches with one run always in flight on every rank (``lbft_run_async`` /
+        ``lbft_wait``): yields one ``ShardedResult`` per batch, in order.  While batch k runs, batch k + 1 is staged in the
+        other pinned seed buffer; when batch k's summaries have landed, its all-gather reads the device buffers, batch k + 1
+        is launched, and only then are batch k's summaries copied into the caller's arrays — the host side of a step
+        overlaps the next kernel.  Local runners without ``run_async`` (the CPU stand-ins of the tests) run one by one."""
+        if not hasattr(self.local, "run_async"):
+            for seeds in batches:
+                self.set_seeds(seeds)
+                yield self.run(strict=strict)
+            return
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return
+        n, on_device = self.hi - self.lo, self._gathers_on_device()
+        box = {}
+
+        def gather_device():
+            box["block"] = self.gather()
+
+        self.set_seeds(first)
+        self.local.run_async()
+        nxt = next(it, None)
+        while True:
+            if nxt is not None:
+                self.set_seeds(nxt)
+            res = self.local.wait(strict=strict, relaunch=nxt is not None, before_relaunch=gather_device if on_device else None)
+            block = box.pop("block", None) if on_device else self.gather(res)
+            yield ShardedResult(res, block, n, self.num_nodes, self.lo, self.hi)
+            if nxt is None:
+                return
+            nxt = next(it, None)
 
     def loop_until(self, max_clock, strict=True):
         """``Simulator::new`` + ``loop_until(max_clock)`` for the whole job (simulator.rs:200-250, 380-475)."""

@@ -276,13 +276,37 @@ class BatchSimulator:
         run's ``BatchResult`` stays valid, and ``set_seeds`` may stage the next batch meanwhile.  Finish with ``wait()``."""
         _lib.check(self._lib.lbft_run_async(self._handle))
 
-    def wait(self, strict=True):
-        """``lbft_wait``: block until the run started by ``run_async`` is done; returns its ``BatchResult``."""
+    def wait(self, strict=True, relaunch=False, before_relaunch=None):
+        """``lbft_wait``: block until the run started by ``run_async`` is done; returns its ``BatchResult``.
+
+        ``relaunch=True`` starts the next run (``lbft_run_async`` on the seeds staged by ``set_seeds`` meanwhile) BEFORE the
+        finished run's summaries are copied out of the pinned mirrors, so that the host-side copies overlap the next
+        kernel: the library keeps two sets of mirrors and the getters serve the finished run while the next one is in
+        flight.  ``before_relaunch()`` runs between the two (the multi-GPU all-gather reads the device buffers there)."""
         self._generation += 1
         code = self._lib.lbft_wait(self._handle)
         _lib.check(code, allow=() if strict else (_lib.LBFT_ERR_CAPACITY,))
         self._read_timing()
+        if before_relaunch is not None:
+            before_relaunch()
+        if relaunch:
+            self.run_async()
         return BatchResult(self)
+
+    def run_stream(self, batches, strict=True):
+        """Run a sequence of seed batches with one run always in flight: yields one ``BatchResult`` per batch, in order.
+        Batch k + 1 is staged (pinned seed buffer) while batch k runs and launched the moment batch k's results have
+        landed; each step still copies its seeds host->device and its summaries device->host."""
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return
+        self.set_seeds(first)
+        self.run_async()
+        for nxt in it:
+            self.set_seeds(nxt)
+            yield self.wait(strict=strict, relaunch=True)
+        yield self.wait(strict=strict)
 
     def device_buffer(self, which):
         """(device pointer, bytes) of a result buffer: 0 commit counts, 1 last states, 2 counters, 3 status."""

@@ -42,6 +42,10 @@ np.save(os.path.join(%(out)r, "rounds_%%d.npy" %% rank), res.active_rounds)
 sim.set_seeds(seeds + 1000)          # re-seed the whole job: every rank keeps its own contiguous shard
 res2 = sim.run()
 np.save(os.path.join(%(out)r, "counts2_%%d.npy" %% rank), res2.commit_counts)
+streamed = list(sim.run_stream([seeds, seeds + 1000]))   # (this stand-in has no run_async: one run after the other)
+assert len(streamed) == 2
+assert (streamed[0].commit_counts == res.commit_counts).all() and (streamed[1].commit_counts == res2.commit_counts).all()
+assert (streamed[1].last_committed_states == res2.last_committed_states).all()
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -93,3 +97,52 @@ def test_functional_form_and_uneven_batches():
     seeds = np.arange(10, 18, dtype=np.uint64)
     counts, states = run_sharded(seeds, 3, 1000, 0, 1, lambda s: (np.tile(s[:, None], (1, 3)), np.tile(s[:, None] * 2, (1, 3))))
     assert counts.shape == (8, 3) and (counts[:, 0] == seeds).all() and (states[:, 2] == seeds * 2).all()
+
+
+class _AsyncHostLocal:
+    """A local runner with the asynchronous surface of BatchSimulator (set_seeds / run_async / wait(relaunch, before_relaunch)),
+    the host-compiled core doing the work at wait(): checks the ORDER ShardedBatchSimulator.run_stream drives it in."""
+
+    def __init__(self, hc, log):
+        self.hc, self.log, self.staged, self.inflight = hc, log, None, None
+
+    def create(self, max_clock):
+        self.max_clock = max_clock
+        return self
+
+    def close(self):
+        pass
+
+    def set_seeds(self, shard):
+        self.log.append("stage")
+        self.staged = np.array(shard)
+
+    def run_async(self):
+        assert self.inflight is None, "two runs in flight"
+        self.log.append("launch")
+        self.inflight = self.staged
+
+    def wait(self, strict=True, relaunch=False, before_relaunch=None):
+        self.log.append("wait")
+        r = self.hc.run(self.inflight, 4, self.max_clock)
+        self.inflight = None
+        r.last_committed_states, r.active_rounds = r.last_states, np.ascontiguousarray(r.counters[:, 6])
+        if before_relaunch is not None:
+            before_relaunch()
+        if relaunch:
+            self.run_async()
+        return r
+
+
+def test_run_stream_stages_the_next_batch_before_waiting(oracle, hostcore):
+    from librabft_simulator_b200.distributed import ShardedBatchSimulator
+    log = []
+    batches = [np.arange(b, b + 16, dtype=np.uint64) for b in (10, 900, 4242)]
+    sim = ShardedBatchSimulator(batches[0], 4, make_local=lambda shard: _AsyncHostLocal(hostcore, log)).create(500)
+    outs = list(sim.run_stream(iter(batches)))
+    assert log == ["stage", "launch", "stage", "wait", "launch", "stage", "wait", "launch", "wait"]
+    for res, b in zip(outs, batches):
+        ref = oracle.run(b, 4, 500)
+        np.testing.assert_array_equal(res.commit_counts, ref.commit_counts)
+        np.testing.assert_array_equal(res.last_committed_states, ref.last_states)
+    assert list(sim.run_stream([])) == []

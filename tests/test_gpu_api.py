@@ -173,3 +173,31 @@ def test_sharded_simulator_single_rank(oracle):
     np.testing.assert_array_equal(res.commit_counts, ref.commit_counts)
     np.testing.assert_array_equal(res.last_committed_states, ref.last_states)
     np.testing.assert_array_equal(res.active_rounds, ref.counters[:, 6])
+
+
+def test_run_stream_keeps_one_run_in_flight_and_matches_the_oracle(oracle):
+    """BatchSimulator.run_stream / ShardedBatchSimulator.run_stream: one result per batch, in order, each bit-exact — the next
+    run is already in flight when a result is handed out, and the counters of the finished run stay readable meanwhile."""
+    from librabft_simulator_b200 import RandomDelay, ShardedBatchSimulator
+    batches = [np.arange(b, b + 96, dtype=np.uint64) for b in (100, 5000, 70000, 123456)]
+    refs = [oracle.run(b, 4, 1000) for b in batches]
+    sim = make(batches[0]).create(1000)
+    got = 0
+    for res, ref in zip(sim.run_stream(batches), refs):
+        np.testing.assert_array_equal(res.commit_counts, ref.commit_counts)
+        np.testing.assert_array_equal(res.last_committed_states, ref.last_states)
+        np.testing.assert_array_equal(res.counters[:, :8], ref.counters[:, :8])   # read while the next batch runs
+        got += 1
+    assert got == len(batches)
+    assert list(sim.run_stream([])) == []
+    res = sim.run()                                   # the handle is idle again after a stream
+    np.testing.assert_array_equal(res.commit_counts, refs[-1].commit_counts)
+    sim.close()
+    sharded = ShardedBatchSimulator(batches[0], 4, RandomDelay.new(10.0, 4.0)).create(1000)
+    outs = list(sharded.run_stream(batches))
+    assert len(outs) == len(batches)
+    for res, ref in zip(outs, refs):
+        np.testing.assert_array_equal(res.commit_counts, ref.commit_counts)
+        np.testing.assert_array_equal(res.last_committed_states, ref.last_states)
+        np.testing.assert_array_equal(res.active_rounds, ref.counters[:, 6])
+    sharded.close()
