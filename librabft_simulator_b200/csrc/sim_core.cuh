@@ -51,15 +51,6 @@
 #ifndef LBFT_ST16
 #define LBFT_ST16 1
 #endif
-// Calendar-queue experiments (profiles/r2t_ab_calendar.txt): prefetch of a send's list head/tail word as soon as its delay is known
-// (thread kernels: the next send's delay is drawn before the current event is queued), and the second entry of the pool's
-// free list kept in a register.
-#ifndef LBFT_PUSH_PF
-#define LBFT_PUSH_PF 0
-#endif
-#ifndef LBFT_CAL_FREE2
-#define LBFT_CAL_FREE2 0
-#endif
 
 namespace lbft {
 
@@ -401,18 +392,6 @@ struct Core {
   uint32_t proc0, proc1, proc2, proc3, cancelled, max_queue, sched_notify, dedup;
   uint32_t win;                 // bitset word index speculatively loaded with the node (hint = last node handled)
   uint32_t cal_t, cal_free, cal_next;  // QMODE 3: current bucket time, pool free list head, pool bump pointer
-  uint32_t cal_free_nx = PAY_NONE;     // LBFT_CAL_FREE2: the entry below the free list's head (its link word, read ahead)
-  static constexpr bool FREE2 = LBFT_CAL_FREE2 != 0 && QMODE == 3;
-  static constexpr bool PUSH_PF = LBFT_PUSH_PF != 0 && QMODE == 3;
-  // the list head/tail word a send at time t will touch: fetched while the delay of the next send is being drawn
-  LBFT_HD void cal_prefetch(int32_t t, uint32_t kind) const {
-#if defined(__CUDA_ARCH__)
-    if (PUSH_PF && t <= P.max_clock) {
-      const size_t ga = __cvta_generic_to_global(m.at(L.cal_ht + (uint32_t)t * 4 + kind));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(ga));
-    }
-#endif
-  }
   int32_t part_until;  // partition plan: part_open holds for every clock below this (0: not computed yet)
   uint64_t part_open;  // ... the windows open in that span, a bit per window
   uint32_t rs_pend;  // recording only: node << 16 | active round of the round switch not yet stamped with a pop time (0: none)
@@ -642,14 +621,8 @@ struct Core {
       // calendar queue: one FIFO list per (time, kind).  Creation stamps grow with every push, so FIFO order inside
       // a list IS stamp order, and the pop below takes kinds in priority order: exactly (time, kind desc, stamp).
       uint32_t e;
-      if (cal_free != PAY_NONE) {
-        e = cal_free;
-        if (FREE2) {  // the new head is already in a register; its own link is read ahead (nothing waits for it until the
-                      // allocation after next, and a release in between makes it moot)
-          cal_free = cal_free_nx;
-          cal_free_nx = cal_free != PAY_NONE ? m.ld(L.heap_time + cal_free) : PAY_NONE;
-        } else cal_free = m.ld(L.heap_time + e);
-      } else e = cal_next++;
+      if (cal_free != PAY_NONE) { e = cal_free; cal_free = m.ld(L.heap_time + e); }
+      else e = cal_next++;
       m.st(L.heap_key + e, data);
       const uint32_t t = (uint32_t)time, kw = t >> 3, sh = (t & 7) * 4 + kind, hw = L.cal_ht + t * 4 + kind;
       uint32_t occ = km_ld(kw);
@@ -717,7 +690,6 @@ struct Core {
       if (e == (ht >> 16)) km_st(kw, km_ld(kw) & ~(1u << ((cal_t & 7) * 4 + kind)));  // list became empty
       else m.st(hw, (ht & 0xffff0000u) | m.ld(L.heap_time + e));
       m.st(L.heap_time + e, cal_free);
-      if (FREE2) cal_free_nx = cal_free;
       cal_free = e;
       time = (int32_t)cal_t;
       qsize--;
@@ -1426,7 +1398,6 @@ struct Core {
     win = 0;
     cc0 = cc1 = cc2 = cc3 = 0;
     cal_t = 0; cal_free = PAY_NONE; cal_next = 0;
-    cal_free_nx = PAY_NONE;
     part_until = 0; part_open = 0;
     if (REC) {
       rs_pend = 0;
@@ -1610,36 +1581,15 @@ struct Core {
         if (staged) {
           for (uint32_t i = 0; i < list.len; i++) ws->z[i] = standard_normal();
           grp_sync();
-          for (uint32_t i = wl; i < list.len; i += G) {
-            const int32_t dl = delay_from_z(ws->z[i]);
-            ws->dly[i] = (uint16_t)dl;
-            cal_prefetch(clock + dl, ev_kind);
-          }
+          for (uint32_t i = wl; i < list.len; i += G) ws->dly[i] = (uint16_t)delay_from_z(ws->z[i]);
           grp_sync();
-        }
-        // PUSH_PF, thread kernels: the delay of send i + 1 is drawn — and its list word prefetched — before send i is queued.
-        // Nothing else draws from the stream or takes a creation stamp between two sends of one pass, so both orders stand.
-        constexpr bool ROT = PUSH_PF && !WIDE;
-        int32_t dnext = 0;
-        if (ROT && !staged) {
-          dnext = sample_delay();
-          cal_prefetch(clock + dnext, ev_kind);
         }
 #pragma unroll 1
         for (uint32_t i = 0; i < list.len; i++) {
           uint32_t other = list.get(i);
           uint32_t ev_recv = to_other ? other : receiver, ev_send = to_other ? receiver : other;
-          bool q;
-          if (staged) q = enqueue_network_event(ev_kind, ev_recv, ev_send, pslot, (int32_t)ws->dly[i]);
-          else if (ROT) {
-            const int32_t dcur = dnext;
-            if (i + 1 < list.len) {
-              dnext = sample_delay();
-              cal_prefetch(clock + dnext, ev_kind);
-            }
-            q = enqueue_network_event(ev_kind, ev_recv, ev_send, pslot, dcur);
-          } else q = schedule_network_event(ev_kind, ev_recv, ev_send, pslot);
-          if (q) queued++;
+          if (staged ? enqueue_network_event(ev_kind, ev_recv, ev_send, pslot, (int32_t)ws->dly[i])
+                     : schedule_network_event(ev_kind, ev_recv, ev_send, pslot)) queued++;
         }
         if (to_other && pslot != PAY_NONE) {
           if (queued) write_notification(receiver, d, pslot, queued, hc);
@@ -1694,7 +1644,6 @@ struct Core {
     pay_free = m.ld(w++); pay_next = m.ld(w++); proc0 = m.ld(w++); proc1 = m.ld(w++); proc2 = m.ld(w++); proc3 = m.ld(w++);
     cancelled = m.ld(w++); max_queue = m.ld(w++); sched_notify = m.ld(w++); dedup = m.ld(w++); win = m.ld(w++);
     cal_t = m.ld(w++); cal_free = m.ld(w++); cal_next = m.ld(w++);
-    cal_free_nx = (FREE2 && cal_free != PAY_NONE) ? m.ld(L.heap_time + cal_free) : PAY_NONE;  // (the links in memory are always current)
     const uint32_t rp = m.ld(w++);
     if (REC) rs_pend = rp;
     cc0 = m.ld(w++); cc1 = m.ld(w++); cc2 = m.ld(w++); cc3 = m.ld(w++);
