@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Write the SASS of selected kernels of csrc/liblbft_b200.so under profiles/ (cuobjdump -sass) plus an opcode census, so
 that the instruction counts quoted in DESIGN.md are checkable.  Usage: python tools/dump_sass.py <tag> <substring> [...]
-e.g.  python tools/dump_sass.py r2 'event_loop_kernelILi16ELi2ELb1' 'wide_kernelILi64ELi3ELb0ELi32ELb0'"""
+e.g.  python tools/dump_sass.py r2 'event_loop_kernelILi16ELi2ELi1ELb0ELb0ELb0ELb0ELi32' 'event_loop_kernelILi16ELi3ELi2ELb0ELb0ELb0ELb0ELi8' \
+          'wide_kernelILi64ELi3ELb0ELi8ELb0ELi3' 'wide_kernelILi16ELi2ELb1ELi32ELb0ELi0'   (the kernels BASELINE configs 3, 5, 4 and 1-2 select)"""
 import collections
 import os
 import re
@@ -37,8 +38,10 @@ for pat in pats:
                 ops[m.group(1).split(".")[0]] += 1
         path = os.path.join(ROOT, "profiles", "%s_sass_%s.txt" % (tag, short))
         with open(path, "w") as f:
-            f.write("// %s\n// %d SASS instructions; cuobjdump -sass %s\n" % (pretty, n, os.path.basename(LIB)))
-            f.write("\n".join(lines) + "\n")
+            f.write("// %s\n// %d SASS instructions; cuobjdump -sass %s\n// (instruction encodings stripped: address, predicate, opcode and "
+                    "operands only)\n" % (pretty, n, os.path.basename(LIB)))
+            kept = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", ln).rstrip() for ln in lines]
+            f.write("\n".join(ln for ln in kept if ln.strip()) + "\n")
         top = ", ".join("%s %d" % kv for kv in ops.most_common(14))
         mem = {k: ops[k] for k in ("LDG", "STG", "LDS", "STS", "LDL", "STL", "LDC", "ATOMG", "RED", "REDUX", "SHFL", "VOTE", "WARPSYNC", "BAR", "MUFU", "DMUL", "DADD", "DSETP", "IMAD", "LOP3")}
         summary.append("%s\n  %d instructions -> %s\n  memory / warp-collective / fp64 opcodes: %s\n  top opcodes: %s\n" % (
