@@ -259,6 +259,33 @@ constexpr NodeTime NODE_TIME_NEVER = INT64_MAX;
 using StateId = int32_t;   // index into LedgerIntern; 0 = empty history
 using BlockId = int32_t;   // stand-in for BlockHash
 using QcId = int32_t;      // stand-in for QuorumCertificateHash
+
+// GlobalTime <-> NodeTime (bft-lib/src/simulator.rs:120-126): a node's clock starts at its startup time.
+using GlobalTime = int64_t;
+inline NodeTime to_node_time(GlobalTime t, GlobalTime startup_time) { return t - startup_time; }
+inline GlobalTime from_node_time(NodeTime t, GlobalTime startup_time) { return t + startup_time; }
+
+// librabft-v2/src/util.rs:8-10
+inline bool is_power2_minus1(size_t x) { return (x & (x + 1)) == 0; }
+// librabft-v2/src/util.rs:12-53: merge two sequences sorted by `cmp` (< 0, 0, > 0); elements that compare Equal are kept once
+// when they are `eq`, both (first sequence's first) otherwise.
+template <class T, class Cmp, class Eq>
+inline std::vector<T> merge_sort(const std::vector<T>& v1, const std::vector<T>& v2, Cmp cmp, Eq eq) {
+  std::vector<T> result;
+  size_t i = 0, j = 0;
+  while (i < v1.size() && j < v2.size()) {
+    const int c = cmp(v1[i], v2[j]);
+    if (c < 0) result.push_back(v1[i++]);
+    else if (c == 0) {
+      if (eq(v1[i], v2[j])) result.push_back(v1[i]);
+      else { result.push_back(v1[i]); result.push_back(v2[j]); }
+      i++; j++;
+    } else result.push_back(v2[j++]);
+  }
+  while (i < v1.size()) result.push_back(v1[i++]);
+  while (j < v2.size()) result.push_back(v2[j++]);
+  return result;
+}
 constexpr QcId QC_INITIAL = -1;
 
 struct Command {
@@ -779,7 +806,6 @@ struct RecordStoreState {
     auto it = current_votes.find(a);
     return it == current_votes.end() ? nullptr : &it->second;
   }
-  static bool is_power2_minus1(size_t x) { return (x & (x + 1)) == 0; }  // util.rs:8-10
   std::set<Round> known_quorum_certificate_rounds() const {  // :766-799
     std::set<Round> result;
     for (QcId start : {highest_quorum_certificate_hash_, highest_commit_certificate_hash.value_or(initial_hash)}) {
@@ -804,19 +830,11 @@ struct RecordStoreState {
     };
     auto c1 = chain(highest_quorum_certificate_hash_);
     auto c2 = chain(highest_commit_certificate_hash.value_or(initial_hash));
-    // util.rs:12-53 merge_sort with cmp = qc2.round.cmp(qc1.round) (descending rounds, dedup equal)
-    std::vector<const QuorumCertificate*> qcs;
-    size_t i = 0, j = 0;
-    while (i < c1.size() && j < c2.size()) {
-      if (c1[i]->round > c2[j]->round) qcs.push_back(c1[i++]);
-      else if (c1[i]->round == c2[j]->round) {
-        if (c1[i]->id == c2[j]->id) qcs.push_back(c1[i]);
-        else { qcs.push_back(c1[i]); qcs.push_back(c2[j]); }
-        i++; j++;
-      } else qcs.push_back(c2[j++]);
-    }
-    while (i < c1.size()) qcs.push_back(c1[i++]);
-    while (j < c2.size()) qcs.push_back(c2[j++]);
+    // record_store.rs:822: merge_sort(chain1, chain2, |qc1, qc2| qc2.round.cmp(&qc1.round)) — descending rounds, equal QCs once
+    using QcPtr = const QuorumCertificate*;
+    std::vector<QcPtr> qcs = merge_sort(
+        c1, c2, [](QcPtr a, QcPtr b) { return b->round < a->round ? -1 : (b->round == a->round ? 0 : 1); },
+        [](QcPtr a, QcPtr b) { return a->id == b->id; });
     std::vector<Record> result;
     for (size_t n = qcs.size(); n-- > 0;) {
       result.push_back(Record::of(*block(qcs[n]->certified_block_hash)));
@@ -1251,7 +1269,7 @@ struct Simulator {
     SimulatedNode& node = nodes[author];
     // save_node (:307-309) has no observable effect in the simulator and is omitted.
     int64_t from_node =
-        actions.next_scheduled_update == NODE_TIME_NEVER ? INT64_MAX : actions.next_scheduled_update + node.startup_time;
+        actions.next_scheduled_update == NODE_TIME_NEVER ? INT64_MAX : from_node_time(actions.next_scheduled_update, node.startup_time);
     int64_t new_scheduled_time = std::max(from_node, clk + 1);
     node.ignore_scheduled_updates_until = new_scheduled_time - 1;
     push_event(new_scheduled_time, EV_TIMER, author, author, -1);
@@ -1325,14 +1343,14 @@ struct Simulator {
             counters.timers_cancelled++;
             continue;
           }
-          NodeUpdateActions actions = node.node.update_node(node.context, clk - node.startup_time);
+          NodeUpdateActions actions = node.node.update_node(node.context, to_node_time(clk, node.startup_time));
           process_node_actions(clk, ev.receiver, actions);
           break;
         }
         case EV_NOTIFY: {
           SimulatedNode& node = nodes[ev.receiver];
           std::optional<DataSyncRequest> result = node.node.handle_notification(node.context, notif_pool[ev.payload]);
-          NodeUpdateActions actions = node.node.update_node(node.context, clk - node.startup_time);
+          NodeUpdateActions actions = node.node.update_node(node.context, to_node_time(clk, node.startup_time));
           if (result) {
             int p = (int)req_pool.size();
             req_pool.push_back(*result);
@@ -1352,9 +1370,9 @@ struct Simulator {
         }
         case EV_RESPONSE: {
           SimulatedNode& node = nodes[ev.receiver];
-          node.node.handle_response(node.context, resp_pool[ev.payload], clk - node.startup_time);
+          node.node.handle_response(node.context, resp_pool[ev.payload], to_node_time(clk, node.startup_time));
           if (payload_free) resp_pool[ev.payload] = DataSyncResponse();
-          NodeUpdateActions actions = node.node.update_node(node.context, clk - node.startup_time);
+          NodeUpdateActions actions = node.node.update_node(node.context, to_node_time(clk, node.startup_time));
           process_node_actions(clk, ev.receiver, actions);
           break;
         }

@@ -4,6 +4,12 @@
 //   librabft-v2/src/unit_tests/node_tests.rs:9-76           (Block + QC insertion moves the hqc)
 //   bft-lib/src/unit_tests/simulated_context_tests.rs:38-129 (happened_before, compute/commit/epoch)
 //   bft-lib/src/unit_tests/configuration_tests.rs:6-47       (count, pick_author KAT, quorum table)
+//   bft-lib/src/unit_tests/simulator_tests.rs:6-12           (GlobalTime <-> NodeTime)
+//   bft-lib/src/unit_tests/base_type_tests.rs:6-9            (Round + usize)
+//   librabft-v2/src/unit_tests/util_tests.rs:6-21            (is_power2_minus1, merge_sort)
+// Not transcribed, nothing of theirs is on the path: data_sync_tests.rs (serde_json round trips of the three message types —
+// the oracle's messages are plain structs, never serialised), record_tests.rs (SignedValue / hash of a Block — the oracle
+// identifies records by creation id), pacemaker_tests.rs (empty).
 #include <cstdarg>
 #include <string>
 
@@ -253,6 +259,24 @@ void test_configuration(Report& rep) {  // configuration_tests.rs:6-47
     CHECK(EpochConfiguration(v).quorum_threshold() == expect[n - 1]);
   }
 }
+void test_time_conversion(Report& rep) {  // simulator_tests.rs:6-12
+  const GlobalTime x = 15, start = 3;
+  CHECK(to_node_time(x, start) == 12);
+  CHECK(from_node_time(12, start) == x);
+}
+void test_round_plus_usize(Report& rep) {  // base_type_tests.rs:6-9
+  CHECK(Round(3) + 4 == Round(7));
+}
+void test_util(Report& rep) {  // util_tests.rs:6-21
+  CHECK(is_power2_minus1(1));
+  CHECK(is_power2_minus1(3));
+  CHECK(is_power2_minus1(7));
+  CHECK(!is_power2_minus1(8));
+  CHECK(!is_power2_minus1(2));
+  auto cmp = [](uint64_t a, uint64_t b) { return a < b ? -1 : (a == b ? 0 : 1); };  // u64::cmp
+  auto eq = [](uint64_t a, uint64_t b) { return a == b; };
+  CHECK((merge_sort(std::vector<uint64_t>{0, 2, 6, 9}, std::vector<uint64_t>{2, 5, 6}, cmp, eq) == std::vector<uint64_t>{0, 2, 5, 6, 9}));
+}
 }  // namespace
 
 extern "C" int lbfo_selftest(char* buf, size_t cap) {
@@ -268,6 +292,9 @@ extern "C" int lbfo_selftest(char* buf, size_t cap) {
     test_node(rep);
     test_simulated_context(rep);
     test_configuration(rep);
+    test_time_conversion(rep);
+    test_round_plus_usize(rep);
+    test_util(rep);
   } catch (const std::exception& e) {
     rep.failures++;
     rep.text += std::string("EXCEPTION: ") + e.what() + "\n";
