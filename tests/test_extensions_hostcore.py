@@ -75,3 +75,27 @@ def test_partitions_change_results_but_not_the_main_stream_seeding(oracle):
     # first timer events fire identically -> identical results when the windows are empty
     c = oracle.run(seeds, 7, 1000, partition_windows=0, partition_max_len=300)
     np.testing.assert_array_equal(a.last_states, c.last_states)
+
+
+def test_silent_elision_is_exact_in_every_combination(oracle, hostcore):
+    """Events addressed to silent nodes are counted at send time and never queued in plain one-shot runs (sim_core.cuh
+    enqueue_network_event); the oracle queues and drops them.  Every counter must still agree — with partitions (a dropped
+    send is not counted), uniform and LogNormal delays, weights, each queue kind — and the modes that keep every pop
+    (recording, resumable, true data-sync) must give the same final results as the plain run."""
+    from tests.support import FLAG_RESUMABLE, FLAG_ROUND_SWITCHES
+    seeds = np.arange(4000, 4012, dtype=np.uint64)
+    cases = [
+        (5, 1500, dict(silent=[0, 1, 0, 0, 0], partition_windows=3, partition_max_len=200)),
+        (7, 1000, dict(silent=[0, 0, 1, 0, 0, 1, 0], delay_kind=1, delay_lo=0, delay_hi=12)),        # zero delays: same-time events
+        (4, 3000, dict(silent=[1, 0, 0, 0], voting_rights=[1, 2, 2, 2])),
+        (9, 800, dict(silent=[0, 0, 0, 1, 0, 0, 0, 1, 0], partition_windows=2, partition_max_len=100)),
+        (20, 400, dict(silent=[1 if i % 4 == 1 else 0 for i in range(20)])),
+        (4, 20000, dict(silent=[0, 0, 1, 0])),                                                      # long horizon: heap queue
+    ]
+    for nodes, max_clock, kw in cases:
+        plain = both(oracle, hostcore, seeds, nodes, max_clock, **kw)
+        for flags in (FLAG_ROUND_SWITCHES, FLAG_RESUMABLE):
+            h = hostcore.run(seeds, nodes, max_clock, flags=flags, **kw)
+            np.testing.assert_array_equal(h.commit_counts, plain.commit_counts)
+            np.testing.assert_array_equal(h.last_states, plain.last_states)
+            np.testing.assert_array_equal(h.counters[:, list(range(8)) + [9]], plain.counters[:, list(range(8)) + [9]])
