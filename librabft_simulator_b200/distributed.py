@@ -168,16 +168,23 @@ class ShardedBatchSimulator:
 
         self.set_seeds(first)
         self.local.run_async()
-        nxt = next(it, None)
-        while True:
-            if nxt is not None:
-                self.set_seeds(nxt)
-            res = self.local.wait(strict=strict, relaunch=nxt is not None, before_relaunch=gather_device if on_device else None)
-            block = box.pop("block", None) if on_device else self.gather(res)
-            yield ShardedResult(res, block, n, self.num_nodes, self.lo, self.hi)
-            if nxt is None:
-                return
+        inflight = True
+        try:
             nxt = next(it, None)
+            while True:
+                if nxt is not None:
+                    self.set_seeds(nxt)
+                inflight = False
+                res = self.local.wait(strict=strict, relaunch=nxt is not None, before_relaunch=gather_device if on_device else None)
+                inflight = nxt is not None
+                block = box.pop("block", None) if on_device else self.gather(res)
+                yield ShardedResult(res, block, n, self.num_nodes, self.lo, self.hi)
+                if nxt is None:
+                    return
+                nxt = next(it, None)
+        finally:
+            if inflight and hasattr(self.local, "drain"):  # the consumer stopped early: leave the handle idle
+                self.local.drain()
 
     def loop_until(self, max_clock, strict=True):
         """``Simulator::new`` + ``loop_until(max_clock)`` for the whole job (simulator.rs:200-250, 380-475)."""

@@ -303,10 +303,24 @@ class BatchSimulator:
             return
         self.set_seeds(first)
         self.run_async()
-        for nxt in it:
-            self.set_seeds(nxt)
-            yield self.wait(strict=strict, relaunch=True)
-        yield self.wait(strict=strict)
+        inflight = True
+        try:
+            for nxt in it:
+                self.set_seeds(nxt)
+                inflight = False
+                res = self.wait(strict=strict, relaunch=True)
+                inflight = True
+                yield res
+            inflight = False
+            yield self.wait(strict=strict)
+        finally:
+            if inflight:  # the consumer stopped early (or a batch failed to stage): drain the run that is still in flight
+                self.drain()
+
+    def drain(self):
+        """Wait for an in-flight ``run_async`` and discard its result, leaving the handle idle (no-op if there is none)."""
+        if self._handle is not None and self._lib.lbft_wait(self._handle) == _lib.LBFT_OK:
+            self._generation += 1
 
     def device_buffer(self, which):
         """(device pointer, bytes) of a result buffer: 0 commit counts, 1 last states, 2 counters, 3 status."""

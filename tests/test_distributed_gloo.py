@@ -133,6 +133,10 @@ class _AsyncHostLocal:
             self.run_async()
         return r
 
+    def drain(self):
+        self.log.append("drain")
+        self.inflight = None
+
 
 def test_run_stream_stages_the_next_batch_before_waiting(oracle, hostcore):
     from librabft_simulator_b200.distributed import ShardedBatchSimulator
@@ -146,3 +150,9 @@ def test_run_stream_stages_the_next_batch_before_waiting(oracle, hostcore):
         np.testing.assert_array_equal(res.commit_counts, ref.commit_counts)
         np.testing.assert_array_equal(res.last_committed_states, ref.last_states)
     assert list(sim.run_stream([])) == []
+    # a consumer that stops early leaves no run in flight
+    del log[:]
+    stream = sim.run_stream(iter(batches))
+    next(stream)
+    stream.close()
+    assert log == ["stage", "launch", "stage", "wait", "launch", "drain"] and sim.local.inflight is None
